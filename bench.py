@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""bench.py -- spectra/s deconvolved (2^17 points) on B200, BASELINE.json's headline metric.
+
+One step = one pass of the whole deconvolution hot path (smooth -> detect -> select -> fit -> MSE)
+over one batch of synthetic spectra (SURVEY.md §8d, config 5 by default: ~2,000 selected peaks
+per spectrum).  Spectra are independent, so N GPUs = N processes, each with its own shard, no
+collective on the data path (torch.distributed is used only for the barrier and the max-over-ranks
+of the step time).
+
+  value : whole-job spectra/s with the inputs already resident in HBM (C ABI, MDB_MEM_DEVICE)
+  e2e   : the same through the C ABI with HOST buffers (pinned), H2D + compute + D2H all timed
+  roofline / roofline_hbm : dominant FP64 kernel and the streaming detection kernel, timed live
+          with CUDA events on the launching stream (mdb_profile_*), see DESIGN.md
+  cpu_baseline : the oracle (C port of the reference path, OpenMP over spectra) on a bounded
+          sample of the same workload, rank 0, N=1 only
+
+`--impl reference` times the reference's CPU algorithm (the same oracle port; the Rust reference
+cannot be built in this image) on the host cores and prints the same JSON shape.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+N_POINTS = 131072
+X_MAX, X_WIDTH = 14.81146, 20.0236139622347
+SB = (11.8, -2.2)
+WORKLOADS = {
+    # name: (true lorentzians K, hw range, description)
+    "config5": (3000, (3e-4, 1.5e-3), "synthetic 2^17-pt spectra, K=3000 lorentzians + N(0,300) noise (~2,100 selected peaks)"),
+    "config3": (500, (5e-4, 3e-3), "synthetic 2^17-pt spectra, K=500 lorentzians + N(0,300) noise (~510 selected peaks)"),
+}
+FP64_LANES_PER_SM, N_SM = 64, 148
+FP64_INSTR_PER_EVAL = 12  # counted from SASS: sub, mul, add, 8 for the IEEE division, accumulate
+FLOPS_PER_EVAL = 5        # algorithmic: sub, mul, add, div, accumulate
+
+
+def axis(n):
+    i = np.arange(n, dtype=np.float64)
+    return X_MAX - i * X_WIDTH / (float(n) - 1.0)
+
+
+def draw_params(global_index, k, hw_range):
+    """(K,3) array of (sfhw, hw2, maxp) with sfhw = A*hw^2, i.e. height A at the maximum."""
+    rng = np.random.Generator(np.random.PCG64(20260000 + global_index))
+    maxp = rng.uniform(-2.0, 11.6, k)
+    hw = np.exp(rng.uniform(np.log(hw_range[0]), np.log(hw_range[1]), k))
+    amp = np.exp(rng.uniform(np.log(1e4), np.log(1e7), k))
+    return np.ascontiguousarray(np.stack([amp * hw * hw, hw * hw, maxp], axis=1))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def run_reference(args, rank, world):
+    """The reference's CPU algorithm (oracle port, OpenMP over spectra) on the host cores."""
+    if rank != 0:
+        return
+    import oracle as O
+    k_true, hw_range, desc = WORKLOADS[args.workload]
+    cores = O.max_threads()
+    n_sample = args.cpu_sample or max(8, 2 * cores)
+    x = axis(N_POINTS)
+    ys = np.empty((n_sample, N_POINTS))
+    for s in range(n_sample):
+        p = draw_params(s, k_true, hw_range)
+        rng = np.random.Generator(np.random.PCG64(7_000_000 + s))
+        ys[s] = O.superposition_vec(x, p, parallel=True) + rng.normal(0.0, 300.0, N_POINTS)
+    settings = O.Settings()
+    times = []
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        status, lors, mse, nsel = O.par_deconvolute_spectra(settings, x, ys, SB)
+        t1 = time.perf_counter()
+        assert status == O.OK
+        if it >= args.warmup:
+            times.append(t1 - t0)
+    ms = 1e3 * sum(times) / len(times)
+    value = n_sample / (ms / 1e3)
+    sample = f"{n_sample} of the workload's spectra per step, OpenMP over spectra, {cores} threads"
+    line = {
+        "impl": "reference", "metric": "spectra/s deconvolved (2^17 pts)", "value": value, "unit": "spectra/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {desc}", "points": N_POINTS, "spectra_per_step": n_sample,
+                   "mean_selected_peaks": float(np.mean(nsel)), "settings": "Deconvoluter::default()"},
+        "cpu_baseline": {"value": value, "unit": "spectra/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "spectra/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "clocks": None,
+        "note": "oracle/ C port of the reference path (the Rust reference cannot be built here: no cargo/rustc)",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="config5", choices=sorted(WORKLOADS))
+    ap.add_argument("--spectra", type=int, default=2000, help="spectra per GPU per step")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="spectra in the CPU baseline sample (0 = 2 x cores)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from metabodecon_rust_b200 import _lib
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    k_true, hw_range, desc = WORKLOADS[args.workload]
+    S = args.spectra
+    x_np = axis(N_POINTS)
+    x_dev = torch.from_numpy(x_np).to(dev)
+    y_dev = torch.empty((S, N_POINTS), dtype=torch.float64, device=dev)
+    # ---- synthetic batch, generated on the device: clean signal through the library's own
+    # superposition kernel, plus N(0, 300) noise
+    gen = torch.Generator(device=dev)
+    for s in range(S):
+        gi = rank * S + s
+        p = torch.from_numpy(draw_params(gi, k_true, hw_range)).to(dev)
+        st = lib.mdb_superposition_vec(x_dev.data_ptr(), N_POINTS, p.data_ptr(), k_true, y_dev[s].data_ptr(), _lib.MDB_MEM_DEVICE)
+        assert st == 0, _lib.last_error()
+        gen.manual_seed(7_000_000 + gi)
+        y_dev[s] += torch.randn(N_POINTS, generator=gen, dtype=torch.float64, device=dev) * 300.0
+    torch.cuda.synchronize()
+
+    dec = C.c_void_p()
+    assert lib.mdb_deconvoluter_default(C.byref(dec)) == 0
+
+    def make_views(xp, y_rows_ptr):
+        views = (_lib.SpectrumView * S)()
+        for s in range(S):
+            views[s].chemical_shifts = xp
+            views[s].intensities = y_rows_ptr + s * N_POINTS * 8
+            views[s].len = N_POINTS
+            views[s].signal_boundaries[0], views[s].signal_boundaries[1] = SB
+        return views
+
+    dev_views = make_views(x_dev.data_ptr(), y_dev.data_ptr())
+    stats = {}
+
+    def step(views, memory):
+        batch = C.c_void_p()
+        st = lib.mdb_deconvolute_spectra(dec, views, S, memory, C.byref(batch))
+        assert st == 0, _lib.last_error()
+        n_lor = sum(lib.mdb_batch_n_lorentzians(batch, i) for i in range(S))
+        n_pk = sum(lib.mdb_batch_n_peaks(batch, i) for i in range(S))
+        stats["lorentzians"], stats["peaks"] = n_lor, n_pk
+        lib.mdb_batch_free(batch)
+
+    def timed(views, memory, warmup, steps, profile=False):
+        for _ in range(warmup):
+            step(views, memory)
+        if profile:
+            lib.mdb_profile_reset()
+            lib.mdb_profile_enable(1)
+        lib.mdb_reset_kernel_launch_count()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step(views, memory)
+        e1.record()
+        barrier()
+        if profile:
+            lib.mdb_profile_enable(0)
+        ms = e0.elapsed_time(e1) / steps
+        launches = lib.mdb_kernel_launch_count()
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches
+
+    # ---- value: inputs resident in HBM
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms_dev, launches = timed(dev_views, _lib.MDB_MEM_DEVICE, args.warmup, args.steps, profile=True)
+    clocks = sampler.stop()
+    prof = {}
+    for kid, name in enumerate(_lib.KERNEL_NAMES):
+        ms, n, work = C.c_double(), C.c_uint64(), C.c_double()
+        lib.mdb_profile_read(kid, C.byref(ms), C.byref(n), C.byref(work))
+        prof[name] = {"ms": ms.value, "launches": int(n.value), "work": work.value}
+    value = world * S / (ms_dev / 1e3)
+
+    # ---- e2e: host (pinned) buffers through the C ABI, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        y_host = torch.empty((S, N_POINTS), dtype=torch.float64, pin_memory=True)
+        y_host.copy_(y_dev)
+        x_host = torch.from_numpy(x_np.copy()).pin_memory()
+        torch.cuda.synchronize()
+        host_views = make_views(x_host.data_ptr(), y_host.data_ptr())
+        ms_host, _ = timed(host_views, _lib.MDB_MEM_HOST, max(1, args.warmup), args.steps)
+        h2d = S * N_POINTS * 8 + N_POINTS * 8 * max(1, (S + 242) // 243)  # intensities + the axis once per chunk
+        d2h = stats["lorentzians"] * 24 + stats["peaks"] * 12 + S * (8 + 4 + 48)
+        e2e = {"value": world * S / (ms_host / 1e3), "unit": "spectra/s", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_host, "host_memory": "pinned"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- rooflines from the live per-kernel timings
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+    if os.path.exists(peaks_path):
+        with open(peaks_path) as fh:
+            hbm_peak, hbm_src = float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    sm_mhz = clocks["sm_mhz"] if clocks else 1965.0
+    sm_max = clocks["sm_max_mhz"] if clocks else 1965.0
+    fp64_peak_tflops = N_SM * FP64_LANES_PER_SM * 2 * sm_max * 1e6 / 1e12  # FMA = 2 flops, at max clock
+
+    def fp64_roofline(name):
+        p = prof[name]
+        if p["launches"] == 0 or p["ms"] <= 0:
+            return None
+        evals_per_s = p["work"] / (p["ms"] / 1e3)
+        achieved = evals_per_s * FLOPS_PER_EVAL / 1e12
+        pipe_rate = N_SM * FP64_LANES_PER_SM * sm_mhz * 1e6
+        return {"bound": "fp64", "kernel": name, "achieved": achieved, "peak": fp64_peak_tflops, "unit": "TFLOP/s",
+                "frac": achieved / fp64_peak_tflops, "traffic": None,
+                "peak_source": f"computed: {N_SM} SMs x {FP64_LANES_PER_SM} FP64 lanes x 2 x {sm_max:.0f} MHz (not in MEASURED_PEAKS.json)",
+                "evals_per_s": evals_per_s, "evals_per_launch": p["work"] / p["launches"],
+                "ms_per_launch": p["ms"] / p["launches"], "launches": p["launches"],
+                "fp64_pipe_util": evals_per_s * FP64_INSTR_PER_EVAL / pipe_rate,
+                "fp64_pipe_util_note": f"{FP64_INSTR_PER_EVAL} FP64-pipe instructions per evaluation (SASS) at the median SM clock under load ({sm_mhz:.0f} MHz)"}
+
+    def hbm_roofline(name):
+        p = prof[name]
+        if p["launches"] == 0 or p["ms"] <= 0:
+            return None
+        achieved = p["work"] / (p["ms"] / 1e3) / 1e9
+        return {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak, "traffic": None, "peak_source": hbm_src,
+                "bytes_per_launch": p["work"] / p["launches"], "ms_per_launch": p["ms"] / p["launches"],
+                "launches": p["launches"]}
+
+    dominant = max(("mse_superposition", "fit_iter"), key=lambda k: prof[k]["ms"])
+    roofline = fp64_roofline(dominant)
+    other = fp64_roofline("fit_iter" if dominant == "mse_superposition" else "mse_superposition")
+
+    # ---- CPU baseline on a bounded sample + parity of that sample
+    cpu = None
+    parity = None
+    if not args.no_cpu_baseline and world == 1:
+        import oracle as O
+        cores = O.max_threads()
+        n_sample = min(S, args.cpu_sample or max(8, 2 * cores))
+        ys = y_dev[:n_sample].cpu().numpy()
+        O.par_deconvolute_spectra(O.Settings(), x_np, ys[:min(n_sample, cores)], SB)  # warm-up
+        t0 = time.perf_counter()
+        status, lors, mse, nsel = O.par_deconvolute_spectra(O.Settings(), x_np, ys, SB)
+        dt = time.perf_counter() - t0
+        cpu = {"value": n_sample / dt, "unit": "spectra/s", "cores": cores, "kind": "port",
+               "sample": f"first {n_sample} spectra of the batch, oracle port with OpenMP over spectra, {dt:.1f} s"}
+        # parity of the sample: GPU (device-resident path) vs oracle, bit patterns
+        sub = (_lib.SpectrumView * n_sample)(*[dev_views[i] for i in range(n_sample)])
+        batch = C.c_void_p()
+        assert lib.mdb_deconvolute_spectra(dec, sub, n_sample, _lib.MDB_MEM_DEVICE, C.byref(batch)) == 0
+        ok = status == O.OK
+        for i in range(n_sample):
+            k = lib.mdb_batch_n_lorentzians(batch, i)
+            got = np.ctypeslib.as_array(C.cast(lib.mdb_batch_lorentzians(batch, i), C.POINTER(C.c_double)), (max(k, 1), 3))[:k]
+            ok = ok and k == len(lors[i]) and np.array_equal(got.view(np.uint64), lors[i].view(np.uint64))
+            ok = ok and lib.mdb_batch_mse(batch, i) == mse[i] and lib.mdb_batch_n_peaks(batch, i) == nsel[i]
+        lib.mdb_batch_free(batch)
+        parity = {"spectra": n_sample, "bit_exact_vs_oracle": bool(ok)}
+
+    line = {
+        "metric": "spectra/s deconvolved (2^17 pts)", "value": value, "unit": "spectra/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {desc}", "points": N_POINTS, "spectra_per_gpu_per_step": S,
+                   "mean_selected_peaks": stats["peaks"] / S, "mean_lorentzians": stats["lorentzians"] / S,
+                   "settings": "Deconvoluter::default()", "parallelism": f"spectra sharded over {world} GPU(s), no collective",
+                   "l2": f"inputs {S * N_POINTS * 8 / 2**20:.0f} MiB per GPU per step, larger than the 126 MB L2"},
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": roofline, "roofline_other_fp64": other,
+        "roofline_hbm": {"detect": hbm_roofline("detect"), "smooth": hbm_roofline("smooth")},
+        "kernel_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items() if v["launches"]},
+        "cpu_baseline": cpu, "parity_sample": parity,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,1286 @@
+// api.cu -- host side of libmdb200.so: the C ABI of include/mdb200.h, the Deconvoluter settings
+// logic (validation, ignore-region merge, ppm -> index helpers) and the chunked GPU pipeline.
+//
+// There is no CPU compute path in this file: every stage of the deconvolution runs in the
+// kernels of kernels.cuh, and every entry point fails with MDB_ERR_CUDA when no device is usable.
+//
+// Reference citations are relative to /root/reference/metabodecon/src/.
+#include "../../include/mdb200.h"
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <atomic>
+#include <climits>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <utility>
+#include <vector>
+
+using namespace mdb;
+
+// ---------------------------------------------------------------------------------------------
+// errors, counters
+// ---------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+static std::atomic<uint64_t> g_launches{0};
+
+static mdb_status fail(mdb_status st, const std::string &msg)
+{
+    g_last_error = msg;
+    return st;
+}
+
+#define CUDA_TRY(expr)                                                                            \
+    do {                                                                                          \
+        cudaError_t e__ = (expr);                                                                 \
+        if (e__ != cudaSuccess) {                                                                 \
+            return fail(MDB_ERR_CUDA, std::string(#expr) + " failed: " + cudaGetErrorString(e__)  \
+                                          + " (" __FILE__ ":" + std::to_string(__LINE__) + ")");  \
+        }                                                                                         \
+    } while (0)
+
+#define LAUNCH_CHECK()                                                                            \
+    do {                                                                                          \
+        ++g_launches;                                                                             \
+        CUDA_TRY(cudaGetLastError());                                                             \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// Optional per-kernel timing (bench.py's roofline numbers): CUDA events recorded on the stream the
+// kernel is launched on, resolved when the chunk is finished.  Off by default.
+// ---------------------------------------------------------------------------------------------
+static std::atomic<int> g_profile{0};
+struct ProfAcc { double ms = 0.0; uint64_t launches = 0; double work = 0.0; };
+static std::mutex g_prof_mutex;
+static ProfAcc g_prof[MDB_KERNEL_COUNT];
+struct ProfSpan { int kernel; cudaEvent_t e0, e1; double work; };
+
+static void prof_begin(std::vector<ProfSpan> *spans, int kernel, cudaStream_t stream)
+{
+    if (!spans || !g_profile.load()) return;
+    ProfSpan sp{kernel, nullptr, nullptr, 0.0};
+    if (cudaEventCreate(&sp.e0) != cudaSuccess || cudaEventCreate(&sp.e1) != cudaSuccess) return;
+    cudaEventRecord(sp.e0, stream);
+    spans->push_back(sp);
+}
+static void prof_end(std::vector<ProfSpan> *spans, cudaStream_t stream, double work)
+{
+    if (!spans || !g_profile.load() || spans->empty()) return;
+    ProfSpan &sp = spans->back();
+    sp.work = work;
+    cudaEventRecord(sp.e1, stream);
+}
+// call after the stream has been synchronised
+static void prof_resolve(std::vector<ProfSpan> *spans)
+{
+    if (!spans) return;
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
+    for (ProfSpan &sp : *spans) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, sp.e0, sp.e1) == cudaSuccess && sp.kernel >= 0 && sp.kernel < MDB_KERNEL_COUNT) {
+            g_prof[sp.kernel].ms += ms;
+            g_prof[sp.kernel].launches += 1;
+            g_prof[sp.kernel].work += sp.work;
+        }
+        cudaEventDestroy(sp.e0);
+        cudaEventDestroy(sp.e1);
+    }
+    spans->clear();
+}
+extern "C" void mdb_profile_enable(int on) { g_profile.store(on ? 1 : 0); }
+extern "C" void mdb_profile_reset(void)
+{
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
+    for (auto &a : g_prof) a = ProfAcc();
+}
+extern "C" mdb_status mdb_profile_read(int kernel, double *ms, uint64_t *launches, double *work)
+{
+    if (kernel < 0 || kernel >= MDB_KERNEL_COUNT) return fail(MDB_ERR_INVALID_ARGUMENT, "unknown kernel id");
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
+    if (ms) *ms = g_prof[kernel].ms;
+    if (launches) *launches = g_prof[kernel].launches;
+    if (work) *work = g_prof[kernel].work;
+    return MDB_OK;
+}
+
+extern "C" uint32_t mdb_abi_version(void) { return MDB200_ABI_VERSION; }
+extern "C" const char *mdb_last_error_message(void) { return g_last_error.c_str(); }
+extern "C" uint64_t mdb_kernel_launch_count(void) { return g_launches.load(); }
+extern "C" void mdb_reset_kernel_launch_count(void) { g_launches.store(0); }
+
+extern "C" int mdb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+extern "C" mdb_status mdb_host_alloc(void **ptr, size_t bytes)
+{
+    if (!ptr) return fail(MDB_ERR_INVALID_ARGUMENT, "mdb_host_alloc: null out pointer");
+    CUDA_TRY(cudaMallocHost(ptr, bytes ? bytes : 1));
+    return MDB_OK;
+}
+
+extern "C" mdb_status mdb_host_free(void *ptr)
+{
+    if (ptr) CUDA_TRY(cudaFreeHost(ptr));
+    return MDB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Rust numeric semantics used by the index helpers
+// ---------------------------------------------------------------------------------------------
+static const double F64_EPSILON = 2.220446049250313e-16;
+static const double CHECK_PRECISION = 1.0e+3 * F64_EPSILON;  // lib.rs:277
+
+static size_t f64_as_usize(double f)  // `as usize`: saturating, NaN -> 0
+{
+    if (!(f == f) || f <= 0.0) return 0;
+    if (f >= 18446744073709551615.0) return SIZE_MAX;
+    return (size_t)f;
+}
+
+static int clamp_idx(size_t v) { return v > (size_t)INT_MAX ? INT_MAX : (int)v; }
+
+// Spectrum::signal_boundaries_indices  spectrum/spectrum.rs:741-746 (step: :633-635)
+static void signal_boundaries_indices(double x0, double x1, double sb0, double sb1, size_t *i0, size_t *i1)
+{
+    const double step = x1 - x0;
+    *i0 = f64_as_usize(std::floor((sb0 - x0) / step));
+    *i1 = f64_as_usize(std::ceil((sb1 - x0) / step));
+}
+
+// Deconvoluter::ignore_region_indices  deconvoluter.rs:865-904
+static std::vector<std::pair<size_t, size_t>>
+ignore_region_indices(double x0, double x1, double sb0, double sb1,
+                      const std::vector<std::pair<double, double>> &regions)
+{
+    std::vector<std::pair<size_t, size_t>> out;
+    const double step = x1 - x0, first = x0;
+    const double lower_boundary = std::fmin(sb0, sb1), upper_boundary = std::fmax(sb0, sb1);
+    size_t b0, b1;
+    signal_boundaries_indices(x0, x1, sb0, sb1, &b0, &b1);
+    const size_t lower = std::min(b0, b1), upper = std::max(b0, b1);
+    for (const auto &reg : regions) {
+        const double start = reg.first, end = reg.second;
+        if ((start < lower_boundary && end < lower_boundary) || (start > upper_boundary && end > upper_boundary))
+            continue;
+        const size_t fi = std::max(f64_as_usize(std::floor((start - first) / step)), lower);
+        const size_t si = std::min(f64_as_usize(std::ceil((end - first) / step)), upper);
+        const size_t lo = std::min(fi, si), hi = std::max(fi, si);
+        if (lo < hi - 1) out.emplace_back(lo, hi);  // usize arithmetic: wraps for hi == 0 (release build)
+    }
+    return out;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Settings validation + Deconvoluter object
+// ---------------------------------------------------------------------------------------------
+static mdb_status validate_smoothing(const mdb_smoothing_settings &s)  // smoother.rs:84-100
+{
+    if (s.kind == MDB_SMOOTHING_IDENTITY) return MDB_OK;
+    if (s.kind != MDB_SMOOTHING_MOVING_AVERAGE)
+        return fail(MDB_ERR_INVALID_SMOOTHING_SETTINGS, "unknown smoothing kind");
+    if (s.iterations == 0 || s.window_size <= 1)
+        return fail(MDB_ERR_INVALID_SMOOTHING_SETTINGS,
+                    "invalid smoothing settings: iterations must be > 0 and window size > 1");
+    return MDB_OK;
+}
+
+static mdb_status validate_selection(const mdb_selection_settings &s)  // selector.rs:82-98
+{
+    if (s.kind == MDB_SELECTION_DETECTOR_ONLY) return MDB_OK;
+    if (s.kind != MDB_SELECTION_NOISE_SCORE_FILTER || s.scoring_method != MDB_SCORING_MINIMUM_SUM)
+        return fail(MDB_ERR_INVALID_SELECTION_SETTINGS, "unknown selection kind or scoring method");
+    if (s.threshold <= 0.0 || !std::isfinite(s.threshold))
+        return fail(MDB_ERR_INVALID_SELECTION_SETTINGS,
+                    "invalid selection settings: threshold must be finite and > 0");
+    return MDB_OK;
+}
+
+static mdb_status validate_fitting(const mdb_fitting_settings &s)  // fitter.rs:76-90
+{
+    if (s.kind != MDB_FITTING_ANALYTICAL) return fail(MDB_ERR_INVALID_FITTING_SETTINGS, "unknown fitting kind");
+    if (s.iterations == 0)
+        return fail(MDB_ERR_INVALID_FITTING_SETTINGS, "invalid fitting settings: iterations must be > 0");
+    return MDB_OK;
+}
+
+struct mdb_deconvoluter {
+    mdb_smoothing_settings smoothing;
+    mdb_selection_settings selection;
+    mdb_fitting_settings fitting;
+    bool has_ignore;
+    std::vector<std::pair<double, double>> ignore;
+};
+
+extern "C" mdb_status mdb_deconvoluter_new(const mdb_smoothing_settings *sm, const mdb_selection_settings *se,
+                                           const mdb_fitting_settings *fi, mdb_deconvoluter **out)
+{
+    if (!sm || !se || !fi || !out) return fail(MDB_ERR_INVALID_ARGUMENT, "mdb_deconvoluter_new: null argument");
+    mdb_status st;
+    if ((st = validate_smoothing(*sm)) != MDB_OK) return st;
+    if ((st = validate_selection(*se)) != MDB_OK) return st;
+    if ((st = validate_fitting(*fi)) != MDB_OK) return st;
+    auto *d = new mdb_deconvoluter();
+    d->smoothing = *sm;
+    d->selection = *se;
+    d->fitting = *fi;
+    d->has_ignore = false;
+    *out = d;
+    return MDB_OK;
+}
+
+extern "C" mdb_status mdb_deconvoluter_default(mdb_deconvoluter **out)
+{
+    // SmoothingSettings::default (smoother.rs:58-65), SelectionSettings::default (selector.rs:59-66),
+    // FittingSettings::default (fitter.rs:59-63)
+    mdb_smoothing_settings sm = {MDB_SMOOTHING_MOVING_AVERAGE, 3, 3};
+    mdb_selection_settings se = {MDB_SELECTION_NOISE_SCORE_FILTER, MDB_SCORING_MINIMUM_SUM, 5.0};
+    mdb_fitting_settings fi = {MDB_FITTING_ANALYTICAL, 10};
+    return mdb_deconvoluter_new(&sm, &se, &fi, out);
+}
+
+extern "C" mdb_status mdb_deconvoluter_clone(const mdb_deconvoluter *src, mdb_deconvoluter **out)
+{
+    if (!src || !out) return fail(MDB_ERR_INVALID_ARGUMENT, "mdb_deconvoluter_clone: null argument");
+    *out = new mdb_deconvoluter(*src);
+    return MDB_OK;
+}
+
+extern "C" void mdb_deconvoluter_free(mdb_deconvoluter *d) { delete d; }
+
+extern "C" mdb_status mdb_deconvoluter_smoothing_settings(const mdb_deconvoluter *d, mdb_smoothing_settings *out)
+{
+    if (!d || !out) return fail(MDB_ERR_INVALID_ARGUMENT, "null argument");
+    *out = d->smoothing;
+    return MDB_OK;
+}
+extern "C" mdb_status mdb_deconvoluter_selection_settings(const mdb_deconvoluter *d, mdb_selection_settings *out)
+{
+    if (!d || !out) return fail(MDB_ERR_INVALID_ARGUMENT, "null argument");
+    *out = d->selection;
+    return MDB_OK;
+}
+extern "C" mdb_status mdb_deconvoluter_fitting_settings(const mdb_deconvoluter *d, mdb_fitting_settings *out)
+{
+    if (!d || !out) return fail(MDB_ERR_INVALID_ARGUMENT, "null argument");
+    *out = d->fitting;
+    return MDB_OK;
+}
+extern "C" int64_t mdb_deconvoluter_ignore_regions(const mdb_deconvoluter *d, double *pairs, size_t cap)
+{
+    if (!d || !d->has_ignore) return -1;
+    for (size_t i = 0; i < d->ignore.size() && i < cap && pairs; ++i) {
+        pairs[2 * i] = d->ignore[i].first;
+        pairs[2 * i + 1] = d->ignore[i].second;
+    }
+    return (int64_t)d->ignore.size();
+}
+
+extern "C" mdb_status mdb_deconvoluter_set_smoothing_settings(mdb_deconvoluter *d, const mdb_smoothing_settings *s)
+{
+    if (!d || !s) return fail(MDB_ERR_INVALID_ARGUMENT, "null argument");
+    mdb_status st = validate_smoothing(*s);
+    if (st == MDB_OK) d->smoothing = *s;
+    return st;
+}
+extern "C" mdb_status mdb_deconvoluter_set_selection_settings(mdb_deconvoluter *d, const mdb_selection_settings *s)
+{
+    if (!d || !s) return fail(MDB_ERR_INVALID_ARGUMENT, "null argument");
+    mdb_status st = validate_selection(*s);
+    if (st == MDB_OK) d->selection = *s;
+    return st;
+}
+extern "C" mdb_status mdb_deconvoluter_set_fitting_settings(mdb_deconvoluter *d, const mdb_fitting_settings *s)
+{
+    if (!d || !s) return fail(MDB_ERR_INVALID_ARGUMENT, "null argument");
+    mdb_status st = validate_fitting(*s);
+    if (st == MDB_OK) d->fitting = *s;
+    return st;
+}
+
+// add_ignore_region  deconvoluter.rs:438-472: order the pair, insert, sort by start, merge
+// neighbours that overlap or touch within CHECK_PRECISION until none is left.
+extern "C" mdb_status mdb_deconvoluter_add_ignore_region(mdb_deconvoluter *d, double a, double b)
+{
+    if (!d) return fail(MDB_ERR_INVALID_ARGUMENT, "null argument");
+    if (!std::isfinite(a) || !std::isfinite(b) || std::fabs(a - b) < CHECK_PRECISION)
+        return fail(MDB_ERR_INVALID_IGNORE_REGION, "invalid ignore region: bounds must be finite and distinct");
+    const std::pair<double, double> reg(std::fmin(a, b), std::fmax(a, b));
+    if (!d->has_ignore) {
+        d->has_ignore = true;
+        d->ignore.assign(1, reg);
+        return MDB_OK;
+    }
+    auto &v = d->ignore;
+    v.push_back(reg);
+    std::sort(v.begin(), v.end(), [](const std::pair<double, double> &p, const std::pair<double, double> &q) {
+        return p.first < q.first;
+    });
+    for (;;) {
+        size_t pos = v.size();
+        for (size_t i = 0; i + 1 < v.size(); ++i) {
+            if (v[i + 1].first < v[i].second || std::fabs(v[i].second - v[i + 1].first) < CHECK_PRECISION) {
+                pos = i;
+                break;
+            }
+        }
+        if (pos == v.size()) break;
+        const std::pair<double, double> combined(std::fmin(v[pos].first, v[pos + 1].first),
+                                                 std::fmax(v[pos].second, v[pos + 1].second));
+        v.erase(v.begin() + pos, v.begin() + pos + 2);
+        v.insert(v.begin() + pos, combined);
+    }
+    return MDB_OK;
+}
+
+extern "C" void mdb_deconvoluter_clear_ignore_regions(mdb_deconvoluter *d)
+{
+    if (!d) return;
+    d->has_ignore = false;
+    d->ignore.clear();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Spectrum::new validation  spectrum/spectrum.rs:179-200, 756-905; meta/monotonicity.rs:29-38
+// ---------------------------------------------------------------------------------------------
+extern "C" mdb_status mdb_spectrum_validate(const double *x, size_t nx, const double *y, size_t ny,
+                                            const double sb[2], double ordered[2])
+{
+    if (!sb || !ordered || (nx && !x) || (ny && !y)) return fail(MDB_ERR_INVALID_ARGUMENT, "null argument");
+    if (nx == 0 || ny == 0) return fail(MDB_ERR_EMPTY_DATA, "empty data");
+    if (nx != ny) return fail(MDB_ERR_DATA_LENGTH_MISMATCH, "chemical shifts and intensities differ in length");
+    if (nx < 2) return fail(MDB_ERR_REFERENCE_PANIC, "a single-point spectrum makes the reference index out of range");
+    const double step = x[1] - x[0];
+    if (std::fabs(step) < CHECK_PRECISION) return fail(MDB_ERR_NON_UNIFORM_SPACING, "step size is zero");
+    for (size_t i = 0; i + 1 < nx; ++i) {
+        const double dd = x[i + 1] - x[i];
+        if (std::fabs(dd - step) > CHECK_PRECISION || !std::isfinite(dd))
+            return fail(MDB_ERR_NON_UNIFORM_SPACING, "chemical shifts are not uniformly spaced at index " + std::to_string(i));
+    }
+    for (size_t i = 0; i < ny; ++i)
+        if (!std::isfinite(y[i])) return fail(MDB_ERR_INVALID_INTENSITIES, "non-finite intensity at index " + std::to_string(i));
+    const bool increasing = x[0] < x[1];
+    const double width = sb[0] - sb[1];
+    if (std::fabs(width) < CHECK_PRECISION || !std::isfinite(width))
+        return fail(MDB_ERR_INVALID_SIGNAL_BOUNDARIES, "signal boundaries are not distinct finite numbers");
+    const double lo = std::fmin(sb[0], sb[1]), hi = std::fmax(sb[0], sb[1]);
+    const double first = x[0], last = x[nx - 1];
+    if (increasing) {
+        ordered[0] = lo; ordered[1] = hi;
+        if (ordered[0] < first || ordered[1] > last)
+            return fail(MDB_ERR_INVALID_SIGNAL_BOUNDARIES, "signal boundaries outside the chemical shift range");
+    } else {
+        ordered[0] = hi; ordered[1] = lo;
+        if (ordered[0] > first || ordered[1] < last)
+            return fail(MDB_ERR_INVALID_SIGNAL_BOUNDARIES, "signal boundaries outside the chemical shift range");
+    }
+    return MDB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Device / pinned buffers and workspaces
+// ---------------------------------------------------------------------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaError_t e = cudaFree(p); p = nullptr; cap = 0; if (e != cudaSuccess) return e; }
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { p = nullptr; return e; }
+        cap = want;
+        return cudaSuccess;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return (T *)p; }
+};
+
+struct PinBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e != cudaSuccess) { p = nullptr; return e; }
+        cap = want;
+        return cudaSuccess;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return (T *)p; }
+};
+
+struct Workspace {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    // stage A
+    DevBuf x, y, ys, tmp, occ, cl, cc, cr, cs, sfr, sel, ig, desc, sel_out;
+    PinBuf h_desc, h_ig, h_sel_out;
+    // stage B
+    DevBuf fdesc, segs, fit_state, par_a, par_b, lor, n_kept, resid, mse, peaks_dense;
+    PinBuf h_fdesc, h_segs, h_lor, h_n_kept, h_mse, h_peaks;
+    void release()
+    {
+        for (DevBuf *b : {&x, &y, &ys, &tmp, &occ, &cl, &cc, &cr, &cs, &sfr, &sel, &ig, &desc, &sel_out, &fdesc,
+                          &segs, &fit_state, &par_a, &par_b, &lor, &n_kept, &resid, &mse, &peaks_dense})
+            b->release();
+        for (PinBuf *b : {&h_desc, &h_ig, &h_sel_out, &h_fdesc, &h_segs, &h_lor, &h_n_kept, &h_mse, &h_peaks})
+            b->release();
+        if (ev_a) cudaEventDestroy(ev_a);
+        if (ev_b) cudaEventDestroy(ev_b);
+        if (stream) cudaStreamDestroy(stream);
+        ev_a = ev_b = nullptr;
+        stream = nullptr;
+    }
+};
+
+// Per-process pool of idle workspaces, keyed by device.  Calls check workspaces out and back in,
+// so concurrent callers (the reference's Deconvoluter is Sync) never share one.
+static std::mutex g_pool_mutex;
+static std::multimap<int, Workspace *> g_pool;
+
+static mdb_status acquire_workspace(Workspace **out)
+{
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    {
+        std::lock_guard<std::mutex> lock(g_pool_mutex);
+        auto it = g_pool.find(dev);
+        if (it != g_pool.end()) {
+            *out = it->second;
+            g_pool.erase(it);
+            return MDB_OK;
+        }
+    }
+    auto *ws = new Workspace();
+    ws->device = dev;
+    cudaError_t e = cudaStreamCreateWithFlags(&ws->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ws->ev_a, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ws->ev_b, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        ws->release();
+        delete ws;
+        return fail(MDB_ERR_CUDA, std::string("cannot create CUDA stream/events: ") + cudaGetErrorString(e));
+    }
+    *out = ws;
+    return MDB_OK;
+}
+
+static void release_workspace(Workspace *ws)
+{
+    if (!ws) return;
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    g_pool.emplace(ws->device, ws);
+}
+
+extern "C" mdb_status mdb_release_workspaces(void)
+{
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    std::vector<Workspace *> mine;
+    {
+        std::lock_guard<std::mutex> lock(g_pool_mutex);
+        auto range = g_pool.equal_range(dev);
+        for (auto it = range.first; it != range.second; ++it) mine.push_back(it->second);
+        g_pool.erase(range.first, range.second);
+    }
+    for (Workspace *ws : mine) {
+        ws->release();
+        delete ws;
+    }
+    return MDB_OK;
+}
+
+static mdb_status require_device()
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(MDB_ERR_CUDA, std::string("no usable CUDA device (this library has no CPU fallback): ")
+                                      + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    }
+    return MDB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-spectrum host bookkeeping
+// ---------------------------------------------------------------------------------------------
+struct HostSpec {
+    const double *x = nullptr, *y = nullptr;  // caller pointers (host or device)
+    size_t n = 0;
+    double sb[2] = {0, 0};
+    double x0 = 0, x1 = 0;
+    int sb_i0 = 0, sb_i1 = 0;
+    std::vector<int> ig;                       // flattened (start, end) index pairs
+    std::vector<std::pair<int, int>> ranges;   // MSE ranges (deconvoluter.rs:828-845)
+    int pre_status = MDB_OK;                   // status known before any launch
+};
+
+struct SpecResult {
+    int status = MDB_OK;
+    std::vector<mdb_lorentzian> lor;
+    std::vector<int32_t> peaks;  // triples
+    double mse = 0.0;
+    SelectOut info{};
+};
+
+struct mdb_batch {
+    std::vector<SpecResult> r;
+};
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Host part of a spectrum that does not depend on the GPU: index helpers, MSE ranges.
+static void precompute_spec(HostSpec &h, const mdb_deconvoluter &dc)
+{
+    size_t i0, i1;
+    signal_boundaries_indices(h.x0, h.x1, h.sb[0], h.sb[1], &i0, &i1);
+    h.sb_i0 = clamp_idx(i0);
+    h.sb_i1 = clamp_idx(i1);
+    std::vector<std::pair<size_t, size_t>> ig;
+    if (dc.has_ignore) ig = ignore_region_indices(h.x0, h.x1, h.sb[0], h.sb[1], dc.ignore);
+    h.ig.clear();
+    for (auto &p : ig) {
+        h.ig.push_back(clamp_idx(p.first));
+        h.ig.push_back(clamp_idx(p.second));
+    }
+    // compute_mse ranges: sb0, [ig start, ig end]*, sb1 paired up (deconvoluter.rs:829-845)
+    std::vector<size_t> pts;
+    pts.push_back(i0);
+    if (dc.has_ignore)
+        for (auto &p : ig) { pts.push_back(p.first); pts.push_back(p.second); }
+    pts.push_back(i1);
+    h.ranges.clear();
+    for (size_t k = 0; k + 1 < pts.size(); k += 2) {
+        const size_t s = pts[k], e = pts[k + 1];
+        if (s > e || e > h.n) { h.pre_status = MDB_ERR_REFERENCE_PANIC; h.ranges.clear(); return; }  // slice panics
+        h.ranges.emplace_back((int)s, (int)e);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The pipeline over one chunk of spectra
+// ---------------------------------------------------------------------------------------------
+struct Chunk {
+    Workspace *ws = nullptr;
+    size_t first = 0, count = 0;       // range in the batch
+    std::vector<SpecDesc> desc;        // host mirror
+    std::vector<FitDesc> fdesc;
+    std::vector<Segment> segs;
+    long long p_total = 0;             // selected peaks in the chunk
+    long long res_total = 0;
+    int max_words = 0, max_slots = 0, max_peaks = 0, max_seg_len = 0;
+    bool stage_b_launched = false;
+    std::vector<ProfSpan> spans;       // per-kernel timing, resolved in finish_chunk
+};
+
+static int smem_optin_limit()
+{
+    static int lim = -1;
+    if (lim < 0) {
+        int dev = 0, v = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        lim = v;
+    }
+    return lim;
+}
+
+// Stage A: inputs -> device, smoothing, detection, selection, counts back to the host.
+static mdb_status stage_a(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_deconvoluter &dc, int memory,
+                          bool skip_smoothing_input_is_smoothed)
+{
+    Workspace &ws = *ck.ws;
+    const size_t S = ck.count;
+    // ---- layout
+    size_t y_elems = 0, slot_elems = 0, word_elems = 0, ig_elems = 0;
+    std::vector<size_t> y_off(S), slot_off(S), word_off(S), ig_off(S);
+    std::map<const double *, size_t> x_map;  // caller x pointer -> element offset in ws.x
+    size_t x_elems = 0;
+    ck.max_words = ck.max_slots = 0;
+    for (size_t s = 0; s < S; ++s) {
+        const HostSpec &h = hs[ck.first + s];
+        y_off[s] = y_elems;
+        y_elems += align_up(h.n, 16);
+        const size_t slots = (h.n + 1) / 2, words = (slots + 31) / 32;
+        slot_off[s] = slot_elems;
+        slot_elems += align_up(slots, 16);
+        word_off[s] = word_elems;
+        word_elems += align_up(words, 4);
+        ig_off[s] = ig_elems;
+        ig_elems += h.ig.size();
+        ck.max_words = std::max(ck.max_words, (int)words);
+        ck.max_slots = std::max(ck.max_slots, (int)slots);
+        if (memory == MDB_MEM_HOST && !x_map.count(h.x)) {
+            x_map[h.x] = x_elems;
+            x_elems += align_up(h.n, 16);
+        }
+    }
+    const bool ma = dc.smoothing.kind == MDB_SMOOTHING_MOVING_AVERAGE && !skip_smoothing_input_is_smoothed;
+    const bool need_tmp = ma && dc.smoothing.iterations >= 2;
+    if (memory == MDB_MEM_HOST) {
+        CUDA_TRY(ws.x.ensure(x_elems * 8));
+        CUDA_TRY(ws.y.ensure(y_elems * 8));
+    }
+    CUDA_TRY(ws.ys.ensure(y_elems * 8));
+    if (need_tmp) CUDA_TRY(ws.tmp.ensure(y_elems * 8));
+    CUDA_TRY(ws.occ.ensure(word_elems * 4));
+    CUDA_TRY(ws.cl.ensure(slot_elems * 4));
+    CUDA_TRY(ws.cc.ensure(slot_elems * 4));
+    CUDA_TRY(ws.cr.ensure(slot_elems * 4));
+    CUDA_TRY(ws.cs.ensure(slot_elems * 8));
+    CUDA_TRY(ws.sfr.ensure(slot_elems * 8));
+    CUDA_TRY(ws.sel.ensure(slot_elems * 12));
+    CUDA_TRY(ws.ig.ensure(std::max<size_t>(ig_elems, 1) * 4));
+    CUDA_TRY(ws.desc.ensure(S * sizeof(SpecDesc)));
+    CUDA_TRY(ws.sel_out.ensure(S * sizeof(SelectOut)));
+    CUDA_TRY(ws.h_desc.ensure(S * sizeof(SpecDesc)));
+    CUDA_TRY(ws.h_ig.ensure(std::max<size_t>(ig_elems, 1) * 4));
+    CUDA_TRY(ws.h_sel_out.ensure(S * sizeof(SelectOut)));
+
+    // ---- descriptors
+    ck.desc.resize(S);
+    int *h_ig = ws.h_ig.as<int>();
+    for (size_t s = 0; s < S; ++s) {
+        const HostSpec &h = hs[ck.first + s];
+        SpecDesc &d = ck.desc[s];
+        if (memory == MDB_MEM_HOST) {
+            d.x = ws.x.as<double>() + x_map[h.x];
+            d.y = ws.y.as<double>() + y_off[s];
+        } else {
+            d.x = h.x;
+            d.y = h.y;
+        }
+        d.ys = ws.ys.as<double>() + y_off[s];
+        d.tmp = need_tmp ? ws.tmp.as<double>() + y_off[s] : nullptr;
+        d.occ = ws.occ.as<uint32_t>() + word_off[s];
+        d.cl = ws.cl.as<int>() + slot_off[s];
+        d.cc = ws.cc.as<int>() + slot_off[s];
+        d.cr = ws.cr.as<int>() + slot_off[s];
+        d.cs = ws.cs.as<double>() + slot_off[s];
+        d.sfr = ws.sfr.as<double>() + slot_off[s];
+        d.sel = ws.sel.as<int>() + 3 * slot_off[s];
+        d.ig = ws.ig.as<int>() + ig_off[s];
+        d.n = (int)h.n;
+        d.n_slots = (int)((h.n + 1) / 2);
+        d.n_words = (d.n_slots + 31) / 32;
+        d.sb0 = h.sb_i0;
+        d.sb1 = h.sb_i1;
+        d.n_ig = (int)(h.ig.size() / 2);
+        d.has_ig = dc.has_ignore ? 1 : 0;
+        d.pad_ = 0;
+        for (size_t q = 0; q < h.ig.size(); ++q) h_ig[ig_off[s] + q] = h.ig[q];
+    }
+    std::memcpy(ws.h_desc.p, ck.desc.data(), S * sizeof(SpecDesc));
+    CUDA_TRY(cudaMemcpyAsync(ws.desc.p, ws.h_desc.p, S * sizeof(SpecDesc), cudaMemcpyHostToDevice, ws.stream));
+    if (ig_elems)
+        CUDA_TRY(cudaMemcpyAsync(ws.ig.p, ws.h_ig.p, ig_elems * 4, cudaMemcpyHostToDevice, ws.stream));
+
+    // ---- inputs to the device (rows that are adjacent on the host and on the device go as one copy)
+    double *y_dst = skip_smoothing_input_is_smoothed ? ws.ys.as<double>() : ws.y.as<double>();
+    if (memory == MDB_MEM_HOST) {
+        for (auto &kv : x_map) {
+            size_t n = 0;
+            for (size_t s = 0; s < S; ++s)
+                if (hs[ck.first + s].x == kv.first) { n = hs[ck.first + s].n; break; }
+            CUDA_TRY(cudaMemcpyAsync(ws.x.as<double>() + kv.second, kv.first, n * 8, cudaMemcpyHostToDevice, ws.stream));
+        }
+        size_t s = 0;
+        while (s < S) {
+            size_t e = s + 1;
+            const HostSpec &h0 = hs[ck.first + s];
+            size_t bytes = h0.n * 8;
+            while (e < S) {
+                const HostSpec &hp = hs[ck.first + e - 1], &hn = hs[ck.first + e];
+                if (hp.n % 16 == 0 && hn.y == hp.y + hp.n) { bytes += hn.n * 8; ++e; }
+                else break;
+            }
+            CUDA_TRY(cudaMemcpyAsync(y_dst + y_off[s], h0.y, bytes, cudaMemcpyHostToDevice, ws.stream));
+            s = e;
+        }
+    } else if (skip_smoothing_input_is_smoothed) {
+        for (size_t s = 0; s < S; ++s)
+            CUDA_TRY(cudaMemcpyAsync(y_dst + y_off[s], hs[ck.first + s].y, hs[ck.first + s].n * 8,
+                                     cudaMemcpyDeviceToDevice, ws.stream));
+    }
+
+    const SpecDesc *d_desc = ws.desc.as<SpecDesc>();
+    // ---- K1 smoothing (deconvoluter.rs:531-532)
+    if (!skip_smoothing_input_is_smoothed) {
+        if (ma) {
+            const int iters = (int)dc.smoothing.iterations, window = (int)dc.smoothing.window_size;
+            double pts = 0.0;
+            for (size_t s = 0; s < S; ++s) pts += (double)ck.desc[s].n;
+            prof_begin(&ck.spans, MDB_KERNEL_SMOOTH, ws.stream);
+            for (int p = 0; p < iters; ++p) {
+                smooth_pass_generic_kernel<<<(unsigned)((S + 31) / 32), 32, 0, ws.stream>>>(d_desc, (int)S, p, iters, window);
+                LAUNCH_CHECK();
+            }
+            prof_end(&ck.spans, ws.stream, 16.0 * pts);  // algorithmic bytes: read 8N + write 8N
+        } else {  // Identity (smoothing/identity.rs): the smoothed copy is the input itself
+            for (size_t s = 0; s < S; ++s)
+                CUDA_TRY(cudaMemcpyAsync(ck.desc[s].ys, ck.desc[s].y, (size_t)ck.desc[s].n * 8,
+                                         cudaMemcpyDeviceToDevice, ws.stream));
+        }
+    }
+    // ---- K2/K3 detection + scoring
+    {
+        dim3 grid((unsigned)((ck.max_slots + DETECT_THREADS - 1) / DETECT_THREADS), (unsigned)S);
+        double pts = 0.0;
+        for (size_t s = 0; s < S; ++s) pts += (double)ck.desc[s].n;
+        prof_begin(&ck.spans, MDB_KERNEL_DETECT, ws.stream);
+        detect_kernel<<<grid, DETECT_THREADS, 0, ws.stream>>>(d_desc);
+        LAUNCH_CHECK();
+        prof_end(&ck.spans, ws.stream, 8.0 * pts);  // algorithmic bytes: read 8N
+    }
+    // ---- K4 selection
+    {
+        const size_t smem = (size_t)3 * ck.max_words * sizeof(int);
+        if ((int)smem + 1024 > smem_optin_limit())
+            return fail(MDB_ERR_UNSUPPORTED, "spectrum too long for the selection kernel's shared-memory masks");
+        if (smem > 40 * 1024)
+            CUDA_TRY(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        prof_begin(&ck.spans, MDB_KERNEL_SELECT, ws.stream);
+        select_kernel<<<(unsigned)S, SELECT_THREADS, smem, ws.stream>>>(d_desc, ws.sel_out.as<SelectOut>(),
+                                                                       dc.selection.kind, dc.selection.threshold);
+        LAUNCH_CHECK();
+        prof_end(&ck.spans, ws.stream, (double)S);
+    }
+    CUDA_TRY(cudaMemcpyAsync(ws.h_sel_out.p, ws.sel_out.p, S * sizeof(SelectOut), cudaMemcpyDeviceToHost, ws.stream));
+    CUDA_TRY(cudaEventRecord(ws.ev_a, ws.stream));
+    return MDB_OK;
+}
+
+static void fit_state_pointers(Workspace &ws, long long p_total, FitState &st)
+{
+    double *base = ws.fit_state.as<double>();
+    const size_t stride = align_up((size_t)std::max<long long>(p_total, 1), 16);
+    double **fields[] = {&st.ox1, &st.ox2, &st.ox3, &st.oy1, &st.oy2, &st.oy3, &st.sx1, &st.sx3, &st.sy1, &st.sy2, &st.sy3};
+    for (size_t i = 0; i < 11; ++i) *fields[i] = base + i * stride;
+    st.pa = ws.par_a.as<double>();
+    st.pb = ws.par_b.as<double>();
+}
+
+// Stage B: fit, retain, MSE, results back to the host.  `trace` (optional, device->host copies
+// after every pass) is used by mdb_stage_fit only.  `with_mse` false skips K7.
+static mdb_status stage_b(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_deconvoluter &dc,
+                          std::vector<SpecResult> &results, bool with_mse, mdb_lorentzian *trace)
+{
+    Workspace &ws = *ck.ws;
+    const size_t S = ck.count;
+    CUDA_TRY(cudaEventSynchronize(ws.ev_a));
+    const SelectOut *so = ws.h_sel_out.as<SelectOut>();
+    ck.fdesc.assign(S, FitDesc{});
+    ck.segs.clear();
+    ck.p_total = 0;
+    ck.res_total = 0;
+    ck.max_peaks = 0;
+    ck.max_seg_len = 0;
+    for (size_t s = 0; s < S; ++s) {
+        SpecResult &r = results[ck.first + s];
+        const HostSpec &h = hs[ck.first + s];
+        r.info = so[s];
+        r.status = (h.pre_status != MDB_OK) ? h.pre_status : so[s].status;
+        FitDesc &f = ck.fdesc[s];
+        f.off = ck.p_total;
+        f.n_peaks = (r.status == MDB_OK) ? so[s].n_selected : 0;
+        f.seg_off = (int)ck.segs.size();
+        f.seg_cnt = 0;
+        if (r.status == MDB_OK && with_mse) {
+            for (auto &rg : h.ranges) {
+                Segment sg;
+                sg.spec = (int)s; sg.start = rg.first; sg.end = rg.second; sg.pad_ = 0;
+                sg.res_off = ck.res_total;
+                ck.res_total += (long long)align_up((size_t)(rg.second - rg.first), 16);
+                ck.max_seg_len = std::max(ck.max_seg_len, rg.second - rg.first);
+                ck.segs.push_back(sg);
+                ++f.seg_cnt;
+            }
+        }
+        ck.p_total += f.n_peaks;
+        ck.max_peaks = std::max(ck.max_peaks, f.n_peaks);
+    }
+    const size_t P = (size_t)std::max<long long>(ck.p_total, 1);
+    const size_t n_seg = ck.segs.size();
+    CUDA_TRY(ws.fdesc.ensure(S * sizeof(FitDesc)));
+    CUDA_TRY(ws.h_fdesc.ensure(S * sizeof(FitDesc)));
+    CUDA_TRY(ws.segs.ensure(std::max<size_t>(n_seg, 1) * sizeof(Segment)));
+    CUDA_TRY(ws.h_segs.ensure(std::max<size_t>(n_seg, 1) * sizeof(Segment)));
+    CUDA_TRY(ws.fit_state.ensure(11 * align_up(P, 16) * 8));
+    CUDA_TRY(ws.par_a.ensure(P * 24));
+    CUDA_TRY(ws.par_b.ensure(P * 24));
+    CUDA_TRY(ws.lor.ensure(P * 24));
+    CUDA_TRY(ws.peaks_dense.ensure(P * 12));
+    CUDA_TRY(ws.n_kept.ensure(S * 4));
+    CUDA_TRY(ws.mse.ensure(S * 8));
+    CUDA_TRY(ws.resid.ensure(std::max<size_t>((size_t)ck.res_total, 1) * 8));
+    CUDA_TRY(ws.h_lor.ensure(P * 24));
+    CUDA_TRY(ws.h_peaks.ensure(P * 12));
+    CUDA_TRY(ws.h_n_kept.ensure(S * 4));
+    CUDA_TRY(ws.h_mse.ensure(S * 8));
+    std::memcpy(ws.h_fdesc.p, ck.fdesc.data(), S * sizeof(FitDesc));
+    CUDA_TRY(cudaMemcpyAsync(ws.fdesc.p, ws.h_fdesc.p, S * sizeof(FitDesc), cudaMemcpyHostToDevice, ws.stream));
+    if (n_seg) {
+        std::memcpy(ws.h_segs.p, ck.segs.data(), n_seg * sizeof(Segment));
+        CUDA_TRY(cudaMemcpyAsync(ws.segs.p, ws.h_segs.p, n_seg * sizeof(Segment), cudaMemcpyHostToDevice, ws.stream));
+    }
+    const SpecDesc *d_desc = ws.desc.as<SpecDesc>();
+    const FitDesc *d_fd = ws.fdesc.as<FitDesc>();
+    FitState st;
+    fit_state_pointers(ws, ck.p_total, st);
+    const int iters = (int)dc.fitting.iterations;
+    const double *final_par = st.pa;
+    if (ck.p_total > 0) {
+        dim3 grid((unsigned)((ck.max_peaks + FIT_THREADS - 1) / FIT_THREADS), (unsigned)S);
+        prof_begin(&ck.spans, MDB_KERNEL_FIT_INIT, ws.stream);
+        fit_init_kernel<<<grid, FIT_THREADS, 0, ws.stream>>>(d_desc, d_fd, st, ws.peaks_dense.as<int>());
+        LAUNCH_CHECK();
+        prof_end(&ck.spans, ws.stream, (double)ck.p_total);
+        double evals_per_pass = 0.0;  // E_fit per pass = 3 * P_s^2
+        for (size_t s = 0; s < S; ++s) evals_per_pass += 3.0 * (double)ck.fdesc[s].n_peaks * (double)ck.fdesc[s].n_peaks;
+        if (trace) {
+            CUDA_TRY(cudaMemcpyAsync(trace, st.pa, (size_t)ck.p_total * 24, cudaMemcpyDeviceToHost, ws.stream));
+        }
+        double *pin = st.pa, *pout = st.pb;
+        for (int it = 0; it < iters; ++it) {
+            prof_begin(&ck.spans, MDB_KERNEL_FIT_ITER, ws.stream);
+            fit_iter_kernel<<<grid, FIT_THREADS, 0, ws.stream>>>(d_fd, st, pin, pout);
+            LAUNCH_CHECK();
+            prof_end(&ck.spans, ws.stream, evals_per_pass);
+            if (trace)
+                CUDA_TRY(cudaMemcpyAsync(trace + (size_t)(it + 1) * ck.p_total, pout, (size_t)ck.p_total * 24,
+                                         cudaMemcpyDeviceToHost, ws.stream));
+            std::swap(pin, pout);
+        }
+        final_par = pin;
+    }
+    prof_begin(&ck.spans, MDB_KERNEL_RETAIN, ws.stream);
+    retain_kernel<<<(unsigned)S, RETAIN_THREADS, 0, ws.stream>>>(d_fd, final_par, ws.lor.as<double>(), ws.n_kept.as<int>());
+    LAUNCH_CHECK();
+    prof_end(&ck.spans, ws.stream, (double)ck.p_total);
+    if (with_mse && n_seg) {
+        const int per_block = SUP_THREADS * SUP_R;
+        dim3 grid((unsigned)((ck.max_seg_len + per_block - 1) / per_block), (unsigned)n_seg);
+        if (grid.x > 0) {
+            prof_begin(&ck.spans, MDB_KERNEL_MSE_SUPERPOSITION, ws.stream);
+            superposition_kernel<1><<<grid, SUP_THREADS, 0, ws.stream>>>(
+                nullptr, 0, nullptr, 0, ws.resid.as<double>(), d_desc, d_fd, ws.segs.as<Segment>(),
+                ws.lor.as<double>(), ws.n_kept.as<int>());
+            LAUNCH_CHECK();
+            prof_end(&ck.spans, ws.stream, -1.0);  // work = sum(points * kept), known in finish_chunk
+        }
+        prof_begin(&ck.spans, MDB_KERNEL_MSE_REDUCE, ws.stream);
+        mse_reduce_kernel<<<(unsigned)((S * 32 + 127) / 128), 128, 0, ws.stream>>>(d_fd, ws.segs.as<Segment>(),
+                                                                                  ws.resid.as<double>(), ws.mse.as<double>(), (int)S);
+        LAUNCH_CHECK();
+        prof_end(&ck.spans, ws.stream, 8.0 * (double)ck.res_total);
+        CUDA_TRY(cudaMemcpyAsync(ws.h_mse.p, ws.mse.p, S * 8, cudaMemcpyDeviceToHost, ws.stream));
+    }
+    CUDA_TRY(cudaMemcpyAsync(ws.h_n_kept.p, ws.n_kept.p, S * 4, cudaMemcpyDeviceToHost, ws.stream));
+    if (ck.p_total > 0) {
+        CUDA_TRY(cudaMemcpyAsync(ws.h_lor.p, ws.lor.p, (size_t)ck.p_total * 24, cudaMemcpyDeviceToHost, ws.stream));
+        CUDA_TRY(cudaMemcpyAsync(ws.h_peaks.p, ws.peaks_dense.p, (size_t)ck.p_total * 12, cudaMemcpyDeviceToHost, ws.stream));
+    }
+    CUDA_TRY(cudaEventRecord(ws.ev_b, ws.stream));
+    ck.stage_b_launched = true;
+    return MDB_OK;
+}
+
+// Wait for stage B and unpack into the batch.
+static mdb_status finish_chunk(Chunk &ck, std::vector<SpecResult> &results, bool with_mse)
+{
+    Workspace &ws = *ck.ws;
+    CUDA_TRY(cudaEventSynchronize(ws.ev_b));
+    const int *kept = ws.h_n_kept.as<int>();
+    const double *mse = ws.h_mse.as<double>();
+    const mdb_lorentzian *lor = ws.h_lor.as<mdb_lorentzian>();
+    const int32_t *pk = ws.h_peaks.as<int32_t>();
+    if (!ck.spans.empty()) {
+        double mse_evals = 0.0;  // E_mse = sum over ranges of points * P_kept (signal-region points only)
+        for (const Segment &sg : ck.segs) mse_evals += (double)(sg.end - sg.start) * (double)kept[sg.spec];
+        for (ProfSpan &sp : ck.spans)
+            if (sp.kernel == MDB_KERNEL_MSE_SUPERPOSITION) sp.work = mse_evals;
+        prof_resolve(&ck.spans);
+    }
+    for (size_t s = 0; s < ck.count; ++s) {
+        SpecResult &r = results[ck.first + s];
+        if (r.status != MDB_OK) continue;
+        const FitDesc &f = ck.fdesc[s];
+        r.lor.assign(lor + f.off, lor + f.off + kept[s]);
+        r.peaks.assign(pk + 3 * f.off, pk + 3 * (f.off + f.n_peaks));
+        r.mse = with_mse ? mse[s] : 0.0;
+    }
+    return MDB_OK;
+}
+
+static size_t chunk_size_for(const std::vector<HostSpec> &hs)
+{
+    size_t max_n = 0;
+    for (auto &h : hs) max_n = std::max(max_n, h.n);
+    const char *env = std::getenv("MDB_CHUNK_SPECTRA");
+    if (env && std::atoi(env) > 0) return (size_t)std::atoi(env);
+    const size_t per_spec = 48 * max_n + 4096;          // device bytes per spectrum
+    const size_t budget = (size_t)1536 << 20;           // per workspace
+    size_t c = budget / per_spec;
+    c = std::max<size_t>(1, std::min<size_t>(c, 512));
+    return c;
+}
+
+// Validate views, fetch x[0], x[1] and run the host-side precompute.
+static mdb_status build_host_specs(const mdb_deconvoluter &dc, const mdb_spectrum_view *sp, size_t n_spec,
+                                   int memory, std::vector<HostSpec> &hs)
+{
+    hs.resize(n_spec);
+    std::map<const double *, std::pair<double, double>> x01;
+    for (size_t s = 0; s < n_spec; ++s) {
+        const mdb_spectrum_view &v = sp[s];
+        if (!v.chemical_shifts || !v.intensities)
+            return fail(MDB_ERR_INVALID_ARGUMENT, "spectrum " + std::to_string(s) + ": null array");
+        if (v.len < 5 || v.len >= ((size_t)1 << 31))
+            return fail(MDB_ERR_INVALID_ARGUMENT, "spectrum " + std::to_string(s) + ": length must be in [5, 2^31)");
+        HostSpec &h = hs[s];
+        h.x = v.chemical_shifts;
+        h.y = v.intensities;
+        h.n = v.len;
+        h.sb[0] = v.signal_boundaries[0];
+        h.sb[1] = v.signal_boundaries[1];
+        auto it = x01.find(h.x);
+        if (it == x01.end()) {
+            double two[2];
+            if (memory == MDB_MEM_HOST) { two[0] = h.x[0]; two[1] = h.x[1]; }
+            else CUDA_TRY(cudaMemcpy(two, h.x, 16, cudaMemcpyDeviceToHost));
+            it = x01.emplace(h.x, std::make_pair(two[0], two[1])).first;
+        }
+        h.x0 = it->second.first;
+        h.x1 = it->second.second;
+        if (dc.smoothing.kind == MDB_SMOOTHING_MOVING_AVERAGE && h.n < dc.smoothing.window_size / 2)
+            h.pre_status = MDB_ERR_REFERENCE_PANIC;  // `values_len - self.right` underflows (moving_average.rs:62)
+        precompute_spec(h, dc);
+    }
+    return MDB_OK;
+}
+
+extern "C" size_t mdb_batch_len(const mdb_batch *b) { return b ? b->r.size() : 0; }
+extern "C" mdb_status mdb_batch_status(const mdb_batch *b, size_t i)
+{
+    return (b && i < b->r.size()) ? (mdb_status)b->r[i].status : MDB_ERR_INVALID_ARGUMENT;
+}
+extern "C" size_t mdb_batch_n_lorentzians(const mdb_batch *b, size_t i) { return (b && i < b->r.size()) ? b->r[i].lor.size() : 0; }
+extern "C" const mdb_lorentzian *mdb_batch_lorentzians(const mdb_batch *b, size_t i)
+{
+    return (b && i < b->r.size()) ? b->r[i].lor.data() : nullptr;
+}
+extern "C" double mdb_batch_mse(const mdb_batch *b, size_t i) { return (b && i < b->r.size()) ? b->r[i].mse : NAN; }
+extern "C" size_t mdb_batch_n_peaks(const mdb_batch *b, size_t i) { return (b && i < b->r.size()) ? b->r[i].peaks.size() / 3 : 0; }
+extern "C" const int32_t *mdb_batch_peaks(const mdb_batch *b, size_t i)
+{
+    return (b && i < b->r.size()) ? b->r[i].peaks.data() : nullptr;
+}
+extern "C" void mdb_batch_free(mdb_batch *b) { delete b; }
+
+static const char *status_text(int st)
+{
+    switch (st) {
+    case MDB_ERR_NO_PEAKS_DETECTED: return "no peaks detected in the spectrum";
+    case MDB_ERR_EMPTY_SIGNAL_REGION: return "no peaks found in the signal region of the spectrum";
+    case MDB_ERR_EMPTY_SIGNAL_FREE_REGION: return "no peaks found in the signal free region of the spectrum";
+    case MDB_ERR_REFERENCE_PANIC: return "input on which the reference implementation panics";
+    default: return "error";
+    }
+}
+
+extern "C" mdb_status mdb_deconvolute_spectra(const mdb_deconvoluter *d, const mdb_spectrum_view *spectra,
+                                              size_t n_spectra, int memory, mdb_batch **out)
+{
+    if (out) *out = nullptr;
+    if (!d || !out || (n_spectra && !spectra)) return fail(MDB_ERR_INVALID_ARGUMENT, "mdb_deconvolute_spectra: null argument");
+    if (memory != MDB_MEM_HOST && memory != MDB_MEM_DEVICE) return fail(MDB_ERR_INVALID_ARGUMENT, "unknown memory kind");
+    mdb_status st = require_device();
+    if (st != MDB_OK) return st;
+    std::unique_ptr<mdb_batch> batch(new mdb_batch());
+    batch->r.resize(n_spectra);
+    if (n_spectra == 0) { *out = batch.release(); return MDB_OK; }
+    std::vector<HostSpec> hs;
+    if ((st = build_host_specs(*d, spectra, n_spectra, memory, hs)) != MDB_OK) return st;
+
+    // Three workspaces in flight: stage A of chunk k+1 is queued before the host waits for the
+    // counts of chunk k, and chunk k-1 is unpacked while chunk k runs its fit / MSE kernels.
+    const size_t csz = chunk_size_for(hs);
+    const size_t n_chunks = (n_spectra + csz - 1) / csz;
+    const size_t n_ws = std::min<size_t>(3, n_chunks);
+    std::vector<Workspace *> wss(n_ws, nullptr);
+    auto cleanup = [&]() {
+        for (Workspace *w : wss)
+            if (w) { cudaStreamSynchronize(w->stream); release_workspace(w); }
+    };
+    for (size_t i = 0; i < n_ws; ++i)
+        if ((st = acquire_workspace(&wss[i])) != MDB_OK) { cleanup(); return st; }
+    std::vector<Chunk> chunks(n_chunks);
+    for (size_t k = 0; k < n_chunks; ++k) {
+        chunks[k].ws = wss[k % n_ws];
+        chunks[k].first = k * csz;
+        chunks[k].count = std::min(csz, n_spectra - k * csz);
+    }
+    st = stage_a(chunks[0], hs, *d, memory, false);
+    for (size_t k = 0; st == MDB_OK && k < n_chunks; ++k) {
+        if (k + 1 < n_chunks) {
+            if (k + 1 >= n_ws) st = finish_chunk(chunks[k + 1 - n_ws], batch->r, true);  // frees that workspace
+            if (st == MDB_OK) st = stage_a(chunks[k + 1], hs, *d, memory, false);
+        }
+        if (st == MDB_OK) st = stage_b(chunks[k], hs, *d, batch->r, true, nullptr);
+    }
+    for (size_t k = (n_chunks >= n_ws ? n_chunks - n_ws : 0); st == MDB_OK && k < n_chunks; ++k)
+        if (chunks[k].stage_b_launched) st = finish_chunk(chunks[k], batch->r, true);
+    cleanup();
+    if (st != MDB_OK) return st;
+    mdb_status first = MDB_OK;
+    for (size_t s = 0; s < n_spectra; ++s)
+        if (batch->r[s].status != MDB_OK) {
+            first = (mdb_status)batch->r[s].status;
+            fail(first, "spectrum " + std::to_string(s) + ": " + status_text(first));
+            break;
+        }
+    *out = batch.release();
+    return first;
+}
+
+// ---------------------------------------------------------------------------------------------
+// superposition_vec
+// ---------------------------------------------------------------------------------------------
+extern "C" mdb_status mdb_superposition_vec(const double *x, size_t n, const mdb_lorentzian *lor, size_t p,
+                                            double *out, int memory)
+{
+    if ((n && (!x || !out)) || (p && !lor)) return fail(MDB_ERR_INVALID_ARGUMENT, "mdb_superposition_vec: null argument");
+    if (p >= ((size_t)1 << 31)) return fail(MDB_ERR_INVALID_ARGUMENT, "too many lorentzians");
+    mdb_status st = require_device();
+    if (st != MDB_OK) return st;
+    if (n == 0) return MDB_OK;
+    Workspace *ws = nullptr;
+    if ((st = acquire_workspace(&ws)) != MDB_OK) return st;
+    struct Guard { Workspace *w; ~Guard() { cudaStreamSynchronize(w->stream); release_workspace(w); } } guard{ws};
+    const double *dx = x, *dl = (const double *)lor;
+    double *dout = out;
+    if (memory == MDB_MEM_HOST) {
+        CUDA_TRY(ws->x.ensure(n * 8));
+        CUDA_TRY(ws->ys.ensure(n * 8));
+        CUDA_TRY(ws->lor.ensure(std::max<size_t>(p, 1) * 24));
+        CUDA_TRY(cudaMemcpyAsync(ws->x.p, x, n * 8, cudaMemcpyHostToDevice, ws->stream));
+        if (p) CUDA_TRY(cudaMemcpyAsync(ws->lor.p, lor, p * 24, cudaMemcpyHostToDevice, ws->stream));
+        dx = ws->x.as<double>();
+        dl = ws->lor.as<double>();
+        dout = ws->ys.as<double>();
+    }
+    const size_t per_block = (size_t)SUP_THREADS * SUP_R;
+    const size_t blocks = (n + per_block - 1) / per_block;
+    if (blocks > 0x7fffffffull) return fail(MDB_ERR_INVALID_ARGUMENT, "grid too large");
+    std::vector<ProfSpan> spans;
+    prof_begin(&spans, MDB_KERNEL_SUPERPOSITION_VEC, ws->stream);
+    superposition_kernel<0><<<(unsigned)blocks, SUP_THREADS, 0, ws->stream>>>(dx, (long long)n, dl, (int)p, dout, nullptr,
+                                                                             nullptr, nullptr, nullptr, nullptr);
+    LAUNCH_CHECK();
+    prof_end(&spans, ws->stream, (double)n * (double)p);
+    if (memory == MDB_MEM_HOST) CUDA_TRY(cudaMemcpyAsync(out, dout, n * 8, cudaMemcpyDeviceToHost, ws->stream));
+    CUDA_TRY(cudaStreamSynchronize(ws->stream));
+    prof_resolve(&spans);
+    return MDB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stage entry points (parity suite)
+// ---------------------------------------------------------------------------------------------
+extern "C" mdb_status mdb_stage_smooth(const double *values, size_t n, uint64_t iterations, uint64_t window, double *out)
+{
+    if (!values || !out) return fail(MDB_ERR_INVALID_ARGUMENT, "null argument");
+    if (n < 5 || n >= ((size_t)1 << 31)) return fail(MDB_ERR_INVALID_ARGUMENT, "length must be in [5, 2^31)");
+    mdb_smoothing_settings sm = {MDB_SMOOTHING_MOVING_AVERAGE, iterations, window};
+    mdb_status st = validate_smoothing(sm);
+    if (st != MDB_OK) return st;
+    if (n < window / 2) return fail(MDB_ERR_REFERENCE_PANIC, "fewer points than half the window");
+    if ((st = require_device()) != MDB_OK) return st;
+    Workspace *ws = nullptr;
+    if ((st = acquire_workspace(&ws)) != MDB_OK) return st;
+    struct Guard { Workspace *w; ~Guard() { cudaStreamSynchronize(w->stream); release_workspace(w); } } guard{ws};
+    const size_t bytes = align_up(n, 16) * 8;
+    CUDA_TRY(ws->y.ensure(bytes));
+    CUDA_TRY(ws->ys.ensure(bytes));
+    CUDA_TRY(ws->tmp.ensure(bytes));
+    CUDA_TRY(ws->desc.ensure(sizeof(SpecDesc)));
+    SpecDesc d{};
+    d.y = ws->y.as<double>();
+    d.ys = ws->ys.as<double>();
+    d.tmp = ws->tmp.as<double>();
+    d.n = (int)n;
+    CUDA_TRY(cudaMemcpyAsync(ws->y.p, values, n * 8, cudaMemcpyHostToDevice, ws->stream));
+    CUDA_TRY(cudaMemcpyAsync(ws->desc.p, &d, sizeof(d), cudaMemcpyHostToDevice, ws->stream));
+    for (int p = 0; p < (int)iterations; ++p) {
+        smooth_pass_generic_kernel<<<1, 32, 0, ws->stream>>>(ws->desc.as<SpecDesc>(), 1, p, (int)iterations, (int)window);
+        LAUNCH_CHECK();
+    }
+    CUDA_TRY(cudaMemcpyAsync(out, ws->ys.p, n * 8, cudaMemcpyDeviceToHost, ws->stream));
+    CUDA_TRY(cudaStreamSynchronize(ws->stream));
+    return MDB_OK;
+}
+
+// Runs stage A on one already-smoothed spectrum held on the host.
+static mdb_status stage_a_single(const mdb_deconvoluter &dc, const double *smoothed, size_t n, size_t sb0, size_t sb1,
+                                 int has_ig, const size_t *ig, size_t n_ig, Chunk &ck, std::vector<HostSpec> &hs)
+{
+    hs.assign(1, HostSpec());
+    HostSpec &h = hs[0];
+    h.x = smoothed;  // placeholder axis: detection and selection never read x
+    h.y = smoothed;
+    h.n = n;
+    h.sb_i0 = clamp_idx(sb0);
+    h.sb_i1 = clamp_idx(sb1);
+    if (has_ig)
+        for (size_t q = 0; q < 2 * n_ig; ++q) h.ig.push_back(clamp_idx(ig[q]));
+    mdb_deconvoluter local = dc;
+    local.has_ignore = has_ig != 0;
+    ck.first = 0;
+    ck.count = 1;
+    return stage_a(ck, hs, local, MDB_MEM_HOST, true);
+}
+
+extern "C" mdb_status mdb_stage_detect(const double *smoothed, size_t n, int32_t *peaks, double *scores, size_t cap,
+                                       size_t *n_found)
+{
+    if (!smoothed || !n_found || (cap && (!peaks || !scores))) return fail(MDB_ERR_INVALID_ARGUMENT, "null argument");
+    if (n < 5 || n >= ((size_t)1 << 31)) return fail(MDB_ERR_INVALID_ARGUMENT, "length must be in [5, 2^31)");
+    mdb_status st = require_device();
+    if (st != MDB_OK) return st;
+    mdb_deconvoluter *dc = nullptr;
+    if ((st = mdb_deconvoluter_default(&dc)) != MDB_OK) return st;
+    std::unique_ptr<mdb_deconvoluter> dc_guard(dc);
+    Workspace *ws = nullptr;
+    if ((st = acquire_workspace(&ws)) != MDB_OK) return st;
+    struct Guard { Workspace *w; ~Guard() { cudaStreamSynchronize(w->stream); release_workspace(w); } } guard{ws};
+    Chunk ck;
+    ck.ws = ws;
+    std::vector<HostSpec> hs;
+    if ((st = stage_a_single(*dc, smoothed, n, 0, n, 0, nullptr, 0, ck, hs)) != MDB_OK) return st;
+    // download the slot arrays and walk the occupancy mask in order (test-only path)
+    const SpecDesc &d = ck.desc[0];
+    std::vector<uint32_t> occ(d.n_words);
+    std::vector<int> cl(d.n_slots), cc(d.n_slots), cr(d.n_slots);
+    std::vector<double> cs(d.n_slots);
+    CUDA_TRY(cudaStreamSynchronize(ws->stream));
+    CUDA_TRY(cudaMemcpy(occ.data(), d.occ, (size_t)d.n_words * 4, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(cl.data(), d.cl, (size_t)d.n_slots * 4, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(cc.data(), d.cc, (size_t)d.n_slots * 4, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(cr.data(), d.cr, (size_t)d.n_slots * 4, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(cs.data(), d.cs, (size_t)d.n_slots * 8, cudaMemcpyDeviceToHost));
+    size_t k = 0;
+    for (int w = 0; w < d.n_words; ++w)
+        for (int j = 0; j < 32; ++j)
+            if (occ[w] & (1u << j)) {
+                const int slot = w * 32 + j;
+                if (k < cap) {
+                    peaks[3 * k] = cl[slot]; peaks[3 * k + 1] = cc[slot]; peaks[3 * k + 2] = cr[slot];
+                    scores[k] = cs[slot];
+                }
+                ++k;
+            }
+    *n_found = k;
+    return MDB_OK;
+}
+
+extern "C" mdb_status mdb_stage_select(const mdb_deconvoluter *dc, const double *smoothed, size_t n, size_t sb0,
+                                       size_t sb1, int has_ignore, const size_t *ignore_idx, size_t n_ignore,
+                                       int32_t *peaks, size_t cap, size_t *n_selected, double *mean_sd)
+{
+    if (!dc || !smoothed || !n_selected || (cap && !peaks) || (n_ignore && !ignore_idx))
+        return fail(MDB_ERR_INVALID_ARGUMENT, "null argument");
+    if (n < 5 || n >= ((size_t)1 << 31)) return fail(MDB_ERR_INVALID_ARGUMENT, "length must be in [5, 2^31)");
+    mdb_status st = require_device();
+    if (st != MDB_OK) return st;
+    Workspace *ws = nullptr;
+    if ((st = acquire_workspace(&ws)) != MDB_OK) return st;
+    struct Guard { Workspace *w; ~Guard() { cudaStreamSynchronize(w->stream); release_workspace(w); } } guard{ws};
+    Chunk ck;
+    ck.ws = ws;
+    std::vector<HostSpec> hs;
+    if ((st = stage_a_single(*dc, smoothed, n, sb0, sb1, has_ignore, ignore_idx, n_ignore, ck, hs)) != MDB_OK) return st;
+    CUDA_TRY(cudaEventSynchronize(ws->ev_a));
+    const SelectOut so = ws->h_sel_out.as<SelectOut>()[0];
+    *n_selected = (size_t)so.n_selected;
+    if (mean_sd) { mean_sd[0] = so.mean; mean_sd[1] = so.sd; }
+    if (so.status != MDB_OK) return fail((mdb_status)so.status, status_text(so.status));
+    const size_t ncopy = std::min<size_t>(cap, (size_t)so.n_selected);
+    if (ncopy) CUDA_TRY(cudaMemcpy(peaks, ck.desc[0].sel, ncopy * 12, cudaMemcpyDeviceToHost));
+    return MDB_OK;
+}
+
+extern "C" mdb_status mdb_stage_fit(const double *x, const double *y, size_t n, const int32_t *peaks, size_t n_peaks,
+                                    uint64_t iterations, mdb_lorentzian *out, size_t *n_retained, mdb_lorentzian *trace)
+{
+    if (!x || !y || !n_retained || (n_peaks && (!peaks || !out))) return fail(MDB_ERR_INVALID_ARGUMENT, "null argument");
+    if (n < 5 || n >= ((size_t)1 << 31)) return fail(MDB_ERR_INVALID_ARGUMENT, "length must be in [5, 2^31)");
+    for (size_t q = 0; q < 3 * n_peaks; ++q)
+        if (peaks[q] < 0 || (size_t)peaks[q] >= n) return fail(MDB_ERR_REFERENCE_PANIC, "peak index out of range");
+    mdb_fitting_settings fs = {MDB_FITTING_ANALYTICAL, iterations};
+    mdb_status st = validate_fitting(fs);
+    if (st != MDB_OK) return st;
+    if ((st = require_device()) != MDB_OK) return st;
+    *n_retained = 0;
+    if (n_peaks == 0) return MDB_OK;
+    mdb_deconvoluter *dc = nullptr;
+    if ((st = mdb_deconvoluter_default(&dc)) != MDB_OK) return st;
+    std::unique_ptr<mdb_deconvoluter> dc_guard(dc);
+    dc->fitting = fs;
+    Workspace *ws = nullptr;
+    if ((st = acquire_workspace(&ws)) != MDB_OK) return st;
+    struct Guard { Workspace *w; ~Guard() { cudaStreamSynchronize(w->stream); release_workspace(w); } } guard{ws};
+    // hand-built chunk: x, y and the peak list go straight into the workspace
+    Chunk ck;
+    ck.ws = ws;
+    ck.first = 0;
+    ck.count = 1;
+    const size_t bytes = align_up(n, 16) * 8;
+    CUDA_TRY(ws->x.ensure(bytes));
+    CUDA_TRY(ws->y.ensure(bytes));
+    CUDA_TRY(ws->sel.ensure(n_peaks * 12));
+    CUDA_TRY(ws->desc.ensure(sizeof(SpecDesc)));
+    CUDA_TRY(ws->sel_out.ensure(sizeof(SelectOut)));
+    CUDA_TRY(ws->h_sel_out.ensure(sizeof(SelectOut)));
+    SpecDesc d{};
+    d.x = ws->x.as<double>();
+    d.y = ws->y.as<double>();
+    d.sel = ws->sel.as<int>();
+    d.n = (int)n;
+    ck.desc.assign(1, d);
+    CUDA_TRY(cudaMemcpyAsync(ws->x.p, x, n * 8, cudaMemcpyHostToDevice, ws->stream));
+    CUDA_TRY(cudaMemcpyAsync(ws->y.p, y, n * 8, cudaMemcpyHostToDevice, ws->stream));
+    CUDA_TRY(cudaMemcpyAsync(ws->sel.p, peaks, n_peaks * 12, cudaMemcpyHostToDevice, ws->stream));
+    CUDA_TRY(cudaMemcpyAsync(ws->desc.p, &d, sizeof(d), cudaMemcpyHostToDevice, ws->stream));
+    SelectOut so{};
+    so.status = MDB_OK;
+    so.n_selected = (int)n_peaks;
+    *ws->h_sel_out.as<SelectOut>() = so;
+    CUDA_TRY(cudaEventRecord(ws->ev_a, ws->stream));
+    std::vector<HostSpec> hs(1);
+    hs[0].n = n;
+    std::vector<SpecResult> res(1);
+    if ((st = stage_b(ck, hs, *dc, res, false, trace)) != MDB_OK) return st;
+    if ((st = finish_chunk(ck, res, false)) != MDB_OK) return st;
+    *n_retained = res[0].lor.size();
+    std::memcpy(out, res[0].lor.data(), res[0].lor.size() * sizeof(mdb_lorentzian));
+    return MDB_OK;
+}

@@ -68,6 +68,9 @@ def lib():
         _lib.orc_detect_peaks.restype = C.c_size_t
         _lib.orc_fit_lorentzian.restype = C.c_size_t
         _lib.orc_ignore_region_indices.restype = C.c_size_t
+        _lib.orc_find_right_border.restype = C.c_size_t
+        _lib.orc_find_left_border.restype = C.c_size_t
+        _lib.orc_find_peak_centers.restype = C.c_size_t
     return _lib
 
 
@@ -108,6 +111,38 @@ def detect_peaks(d2) -> np.ndarray:
     l, c, r = (np.zeros(cap, dtype=np.uintp) for _ in range(3))
     n = lib().orc_detect_peaks(_dp(d2), C.c_size_t(d2.size), _sp(l), _sp(c), _sp(r), C.c_size_t(cap))
     return np.stack([l[:n], c[:n], r[:n]], axis=1)
+
+
+def find_right_border(d2_slice) -> int:
+    t = _f64(d2_slice)
+    return lib().orc_find_right_border(_dp(t), C.c_size_t(t.size))
+
+
+def find_left_border(d2_slice) -> int:
+    u = _f64(d2_slice)
+    return lib().orc_find_left_border(_dp(u), C.c_size_t(u.size))
+
+
+def find_peak_centers(d2) -> list:
+    d2 = _f64(d2)
+    out = np.zeros(d2.size + 1, dtype=np.uintp)
+    n = lib().orc_find_peak_centers(_dp(d2), C.c_size_t(d2.size), _sp(out), C.c_size_t(out.size))
+    return out[:n].tolist()
+
+
+def find_peak_borders(d2, centers) -> list:
+    d2 = _f64(d2)
+    c = _usz(centers)
+    out = np.zeros(2 * c.size, dtype=np.uintp)
+    lib().orc_find_peak_borders(_dp(d2), C.c_size_t(d2.size), _sp(c), C.c_size_t(c.size), _sp(out))
+    return [tuple(p) for p in out.reshape(-1, 2).tolist()]
+
+
+def peak_region_boundaries(centers, sb_idx):
+    c = _usz(centers)
+    out = np.zeros(2, dtype=np.uintp)
+    lib().orc_peak_region_boundaries(_sp(c), C.c_size_t(c.size), C.c_size_t(sb_idx[0]), C.c_size_t(sb_idx[1]), _sp(out))
+    return int(out[0]), int(out[1])
 
 
 def score_peak(abs_d2, left: int, center: int, right: int) -> float:

@@ -128,6 +128,43 @@ static size_t find_left_border(const double *u, size_t len)
     return len;
 }
 
+/* Exported forms of the detector's private helpers so that the reference's own unit tests
+ * (detector.rs:170-228) can be replayed against this file verbatim. */
+size_t orc_find_right_border(const double *t, size_t len) { return find_right_border(t, len); }
+size_t orc_find_left_border(const double *u, size_t len) { return find_left_border(u, len); }
+
+/* detector.rs:120-127 */
+size_t orc_find_peak_centers(const double *d2, size_t m, size_t *centers, size_t cap)
+{
+    size_t count = 0;
+    for (size_t i = 0; i + 2 < m; ++i) {
+        const double *w = d2 + i;
+        if (w[1] < 0. && w[1] < w[0] && w[1] < w[2]) {
+            if (count < cap) centers[count] = i + 2;
+            ++count;
+        }
+    }
+    return count;
+}
+
+/* detector.rs:133-146: (left, right) pairs for the given centres, sentinels included */
+void orc_find_peak_borders(const double *d2, size_t m, const size_t *centers, size_t nc, size_t *borders)
+{
+    for (size_t k = 0; k < nc; ++k) {
+        size_t c = centers[k];
+        borders[2 * k] = c - find_left_border(d2, c);
+        borders[2 * k + 1] = c + find_right_border(d2 + (c - 1), m - (c - 1));
+    }
+}
+
+/* peak_selection/common.rs:26-40, exported for common.rs:61-68 */
+static void peak_region_boundaries(const size_t *center, size_t np, size_t sb0, size_t sb1,
+                                   size_t *out_left, size_t *out_right);
+void orc_peak_region_boundaries(const size_t *center, size_t np, size_t sb0, size_t sb1, size_t *lr)
+{
+    peak_region_boundaries(center, np, sb0, sb1, &lr[0], &lr[1]);
+}
+
 /* peak_selection/detector.rs:99-127  -> triplets ascending by centre.  Returns count; if it
  * exceeds cap only the first cap are stored.  m = len(d2). */
 size_t orc_detect_peaks(const double *d2, size_t m, size_t *left, size_t *center, size_t *right,

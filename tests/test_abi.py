@@ -1,0 +1,148 @@
+"""CPU-side checks of the C-ABI boundary: the library loads, exports every symbol the header
+declares, and the host logic that needs no GPU (settings validation, ignore-region merge,
+Spectrum validation, loud failure without a device) behaves like the reference."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from metabodecon_rust_b200 import Deconvoluter, Spectrum, _lib, exceptions
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    text = open(os.path.join(ROOT, "include", "mdb200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mdb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    declared = header_functions()
+    assert len(declared) >= 35
+    bound = {name for name, _, _ in _lib.SIGNATURES}
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/mdb200.h but not exported"
+        assert name in bound, f"{name} declared in include/mdb200.h but not bound in _lib.SIGNATURES"
+    assert bound <= set(declared)
+    assert lib.mdb_abi_version() == 1
+
+
+def test_struct_layouts_match_the_header():
+    assert C.sizeof(_lib.Lorentzian3) == 24        # lorentzian.rs:138-145: three f64
+    assert C.sizeof(_lib.SmoothingSettings) == 24
+    assert C.sizeof(_lib.SelectionSettings) == 16
+    assert C.sizeof(_lib.FittingSettings) == 16
+    assert C.sizeof(_lib.SpectrumView) == 40
+
+
+def test_default_settings():  # smoother.rs:58-65, selector.rs:59-66, fitter.rs:59-63
+    d = Deconvoluter()
+    assert d.smoothing_settings() == {"method": "MovingAverage", "iterations": 3, "windowSize": 3}
+    assert d.selection_settings() == {"method": "NoiseScoreFilter", "scoringMethod": {"method": "MinimumSum"}, "threshold": 5.0}
+    assert d.fitting_settings() == {"method": "Analytical", "iterations": 10}
+    assert d.ignore_regions() is None
+
+
+def test_settings_validation():  # deconvoluter.rs:919-1010
+    d = Deconvoluter()
+    for it, w in [(0, 3), (3, 0), (3, 1), (0, 0)]:
+        with pytest.raises(exceptions.InvalidSmoothingSettings):
+            d.set_moving_average_smoother(it, w)
+    assert d.smoothing_settings()["iterations"] == 3  # unchanged after a rejected update
+    for thr in (0.0, -1.0, float("inf"), float("nan")):
+        with pytest.raises(exceptions.InvalidSelectionSettings):
+            d.set_noise_score_selector(thr)
+    with pytest.raises(exceptions.InvalidFittingSettings):
+        d.set_analytical_fitter(0)
+    d.set_moving_average_smoother(2, 2)
+    d.set_identity_smoother()
+    assert d.smoothing_settings() == {"method": "Identity"}
+    d.set_detector_only()
+    assert d.selection_settings() == {"method": "DetectorOnly"}
+    d.set_noise_score_selector(6.4)
+    d.set_analytical_fitter(15)
+    assert d.fitting_settings()["iterations"] == 15
+    with pytest.raises(ValueError):
+        d.set_threads(1)
+    d.set_threads(8)
+    d.clear_threads()
+
+
+def test_ignore_region_merge():  # deconvoluter.rs:438-472 and its tests :1012-1115
+    d = Deconvoluter()
+    for bad in [(1.0, 1.0), (float("nan"), 2.0), (1.0, float("inf")), (1.0, 1.0 + 1e-14)]:
+        with pytest.raises(exceptions.InvalidIgnoreRegion):
+            d.add_ignore_region(bad)
+    assert d.ignore_regions() is None
+    d.add_ignore_region((4.9, 4.7))
+    assert d.ignore_regions() == [(4.7, 4.9)]
+    d.add_ignore_region((1.0, 2.0))
+    d.add_ignore_region((7.0, 8.0))
+    assert d.ignore_regions() == [(1.0, 2.0), (4.7, 4.9), (7.0, 8.0)]
+    d.add_ignore_region((4.8, 5.5))          # overlap -> merged
+    assert d.ignore_regions() == [(1.0, 2.0), (4.7, 5.5), (7.0, 8.0)]
+    d.add_ignore_region((2.0, 3.0))          # touching -> merged
+    assert d.ignore_regions() == [(1.0, 3.0), (4.7, 5.5), (7.0, 8.0)]
+    d.add_ignore_region((0.0, 10.0))         # swallows everything
+    assert d.ignore_regions() == [(0.0, 10.0)]
+    d.clear_ignore_regions()
+    assert d.ignore_regions() is None
+
+
+def test_spectrum_validation():  # spectrum.rs:179-200, 756-905
+    x = np.linspace(0.0, 10.0, 101)
+    y = np.ones(101)
+    assert Spectrum(x, y, (9.0, 1.0)).signal_boundaries == (1.0, 9.0)           # re-ordered, increasing axis
+    assert Spectrum(x[::-1], y, (1.0, 9.0)).signal_boundaries == (9.0, 1.0)     # decreasing axis
+    with pytest.raises(exceptions.EmptyData):
+        Spectrum(np.zeros(0), np.zeros(0), (1.0, 2.0))
+    with pytest.raises(exceptions.DataLengthMismatch):
+        Spectrum(x, y[:-1], (1.0, 9.0))
+    bad = x.copy()
+    bad[50] += 1e-3
+    with pytest.raises(exceptions.NonUniformSpacing):
+        Spectrum(bad, y, (1.0, 9.0))
+    with pytest.raises(exceptions.NonUniformSpacing):
+        Spectrum(np.zeros(101), y, (1.0, 9.0))
+    ybad = y.copy()
+    ybad[3] = np.nan
+    with pytest.raises(exceptions.InvalidIntensities):
+        Spectrum(x, ybad, (1.0, 9.0))
+    for sb in [(1.0, 1.0), (-1.0, 9.0), (1.0, 11.0), (float("nan"), 2.0)]:
+        with pytest.raises(exceptions.InvalidSignalBoundaries):
+            Spectrum(x, y, sb)
+
+
+def test_bruker_reader_matches_reference_checks(golden_dir):
+    # macros/check_spectrum.rs:27-50 (check_blood_spectrum!): 2^17 points, range, nucleus, frequency
+    sp = Spectrum.read_bruker(os.path.join(golden_dir, "bruker", "blood_01"), 10, 10, (-2.2, 11.8))
+    assert len(sp) == 131072 and sp.nucleus == "1H"
+    assert abs(sp.chemical_shifts[0] - 14.81146) < 1e-3 and abs(sp.chemical_shifts[-1] - (-5.2121)) < 1e-3
+    assert abs(sp.frequency - 600.252821089118) < 1e-9
+    assert sp.signal_boundaries == (11.8, -2.2)
+    sim = Spectrum.read_bruker(os.path.join(golden_dir, "bruker", "sim_01"), 10, 10, (3.35, 3.55))
+    assert len(sim) == 2048
+
+
+@pytest.mark.skipif(_lib.load().mdb_device_count() > 0, reason="only meaningful without a GPU")
+def test_compute_fails_loudly_without_a_device():
+    x = np.linspace(10.0, 0.0, 100)
+    sp = Spectrum(x, np.ones(100), (9.0, 1.0))
+    with pytest.raises(exceptions.CudaError):
+        Deconvoluter().deconvolute_spectrum(sp)
+    from metabodecon_rust_b200 import Lorentzian
+    with pytest.raises(exceptions.CudaError):
+        Lorentzian.superposition_vec(x, [Lorentzian(1.0, 1.0, 0.0)])
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "metabodecon_rust_b200")
+    for base, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                text = open(os.path.join(base, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text and "mdb_oracle" not in text, f

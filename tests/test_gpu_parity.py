@@ -1,0 +1,441 @@
+"""GPU parity: every stage of the CUDA path against the CPU oracle, through the C ABI.
+
+Bar (BASELINE.json north_star): peak indices and selected-peak sets bit-exact; Lorentzian
+parameters and superposition values within 1e-9 relative.  The kernels replay the reference's
+operation order, so these tests assert the stronger property -- identical bit patterns -- and
+state the 1e-9 tolerance only where a weaker check is all the reference itself could promise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import oracle as O
+import synth
+from metabodecon_rust_b200 import Deconvoluter, Lorentzian, Spectrum, _lib, exceptions
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-9  # north_star tolerance for f64 parameters / superposition values
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float64).view(np.uint64)
+
+
+def assert_bit_equal(got, want, what=""):
+    got = np.ascontiguousarray(got, dtype=np.float64)
+    want = np.ascontiguousarray(want, dtype=np.float64)
+    assert got.shape == want.shape, f"{what}: shape {got.shape} != {want.shape}"
+    neq = bits(got) != bits(want)
+    if neq.any():
+        i = np.flatnonzero(neq.reshape(-1))[0]
+        rel = np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-300))
+        raise AssertionError(f"{what}: {neq.sum()} of {neq.size} values differ in bits; first at {i}: "
+                             f"{got.reshape(-1)[i]!r} vs {want.reshape(-1)[i]!r}; max rel err {rel:.3e} "
+                             f"(north-star tolerance {REL_TOL})")
+
+
+# ------------------------------------------------------------------------------ stage wrappers
+def gpu_smooth(y, iterations, window):
+    lib = _lib.load()
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    out = np.empty_like(y)
+    st = lib.mdb_stage_smooth(y.ctypes.data, y.size, iterations, window, out.ctypes.data)
+    assert st == 0, _lib.last_error()
+    return out
+
+
+def gpu_detect(smoothed):
+    lib = _lib.load()
+    sm = np.ascontiguousarray(smoothed, dtype=np.float64)
+    cap = sm.size // 2 + 2
+    peaks = np.zeros((cap, 3), dtype=np.int32)
+    scores = np.zeros(cap, dtype=np.float64)
+    n = C.c_size_t()
+    st = lib.mdb_stage_detect(sm.ctypes.data, sm.size, peaks.ctypes.data, scores.ctypes.data, cap, C.byref(n))
+    assert st == 0, _lib.last_error()
+    return peaks[:n.value], scores[:n.value]
+
+
+def gpu_select(dec: Deconvoluter, smoothed, sb_idx, ignore_idx=None):
+    lib = _lib.load()
+    sm = np.ascontiguousarray(smoothed, dtype=np.float64)
+    cap = sm.size // 2 + 2
+    peaks = np.zeros((cap, 3), dtype=np.int32)
+    n = C.c_size_t()
+    msd = (C.c_double * 2)()
+    has = ignore_idx is not None
+    ig = np.ascontiguousarray(np.asarray(ignore_idx if has else [], dtype=np.uintp).reshape(-1))
+    st = lib.mdb_stage_select(dec._h, sm.ctypes.data, sm.size, sb_idx[0], sb_idx[1], int(has),
+                              ig.ctypes.data if ig.size else None, ig.size // 2, peaks.ctypes.data, cap,
+                              C.byref(n), msd)
+    return st, peaks[:n.value], (msd[0], msd[1])
+
+
+def gpu_fit(x, y, peaks, iterations, trace=True):
+    lib = _lib.load()
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    pk = np.ascontiguousarray(peaks, dtype=np.int32).reshape(-1, 3)
+    p = pk.shape[0]
+    out = np.zeros((max(p, 1), 3), dtype=np.float64)
+    tr = np.zeros((iterations + 1, max(p, 1), 3), dtype=np.float64)
+    kept = C.c_size_t()
+    st = lib.mdb_stage_fit(x.ctypes.data, y.ctypes.data, x.size, pk.ctypes.data, p, iterations,
+                           out.ctypes.data, C.byref(kept), tr.ctypes.data if trace else None)
+    assert st == 0, _lib.last_error()
+    return out[:kept.value], tr[:, :p]
+
+
+# ------------------------------------------------------------------------------ superposition (K8)
+def test_superposition_reference_kats():
+    # lorentzian.rs:741-788: 11 points x 3 Lorentzians with closed-form expectations
+    lor = [Lorentzian.from_transformed(1.0, 0.5, -2.0), Lorentzian.from_transformed(2.0, 0.75, 0.0),
+           Lorentzian.from_transformed(1.0, 0.5, 2.0)]
+    x = np.array([-5.0 + i for i in range(11)])
+    want = np.array([
+        1.0 / 9.5 + 2.0 / 25.75 + 1.0 / 49.5, 1.0 / 4.5 + 2.0 / 16.75 + 1.0 / 36.5,
+        1.0 / 1.5 + 2.0 / 9.75 + 1.0 / 25.5, 1.0 / 0.5 + 2.0 / 4.75 + 1.0 / 16.5,
+        1.0 / 1.5 + 2.0 / 1.75 + 1.0 / 9.5, 1.0 / 4.5 + 2.0 / 0.75 + 1.0 / 4.5,
+        1.0 / 9.5 + 2.0 / 1.75 + 1.0 / 1.5, 1.0 / 16.5 + 2.0 / 4.75 + 1.0 / 0.5,
+        1.0 / 25.5 + 2.0 / 9.75 + 1.0 / 1.5, 1.0 / 36.5 + 2.0 / 16.75 + 1.0 / 4.5,
+        1.0 / 49.5 + 2.0 / 25.75 + 1.0 / 9.5])
+    for fn in (Lorentzian.superposition_vec, Lorentzian.par_superposition_vec):
+        got = fn(x, lor)
+        np.testing.assert_allclose(got, want, rtol=4e-16)  # float_cmp approx_eq (ULP-level) in the reference
+    for xi, wi in zip(x, want):
+        assert abs(Lorentzian.superposition(float(xi), lor) - wi) <= 4e-16 * abs(wi)
+    # lorentzian.rs:593-604 doc-test
+    trip = [Lorentzian.from_transformed(0.03, 0.0009, 4.8), Lorentzian.from_transformed(0.02, 0.0004, 5.0),
+            Lorentzian.from_transformed(0.03, 0.0009, 5.2)]
+    assert abs(Lorentzian.superposition(5.0, trip) - 51.466992) < 1e-6
+    # lorentzian.rs:707-739 evaluate table
+    one = Lorentzian.from_transformed(1.0, 1.0, 0.0)
+    ev = one.evaluate_vec(x)
+    np.testing.assert_allclose(ev, 1.0 / (1.0 + x * x), rtol=4e-16)
+
+
+@pytest.mark.parametrize("n,p", [(1, 1), (7, 3), (1023, 1), (1025, 1025), (10007, 777), (4096, 2049), (100000, 64)])
+def test_superposition_bit_exact_vs_oracle(n, p):
+    rng = np.random.default_rng(n * 131 + p)
+    x = np.sort(rng.uniform(-2.2, 11.8, n))
+    hw = np.exp(rng.uniform(np.log(5e-4), np.log(3e-3), p))
+    sf = np.exp(rng.uniform(0, np.log(1e4), p))
+    lor = np.stack([sf * hw, hw * hw, rng.uniform(0, 10, p)], axis=1)
+    from metabodecon_rust_b200.lorentzian import superposition_vec_array
+    got = superposition_vec_array(x, lor)
+    want = O.superposition_vec(x, lor)
+    assert_bit_equal(got, want, f"superposition_vec n={n} p={p}")
+
+
+def test_superposition_empty_and_special_values():
+    from metabodecon_rust_b200.lorentzian import superposition_vec_array
+    x = np.linspace(0, 1, 17)
+    got = superposition_vec_array(x, np.zeros((0, 3)))
+    assert np.all(got == 0.0)
+    assert superposition_vec_array(np.zeros(0), np.ones((2, 3))).size == 0
+    # denominators of 0, inf and NaN parameters take the division slow path; compare to the oracle
+    lor = np.array([[1.0, 0.0, 0.5], [np.inf, 1.0, 0.2], [1.0, np.nan, 0.1], [1e-320, 1e300, 0.3], [1e300, 1e-300, 0.7]])
+    for k in range(len(lor)):
+        assert_bit_equal(superposition_vec_array(x, lor[k:k + 1]), O.superposition_vec(x, lor[k:k + 1]), f"special {k}")
+
+
+# ------------------------------------------------------------------------------ smoothing (K1)
+@pytest.mark.parametrize("iterations,window", [(3, 3), (1, 3), (2, 5), (10, 7), (3, 4), (2, 2), (4, 9), (1, 65)])
+def test_smoothing_bit_exact_blood(blood_arrays, iterations, window):
+    _, y = blood_arrays
+    y = y[:40000]
+    assert_bit_equal(gpu_smooth(y, iterations, window), O.smooth_values(y, iterations, window),
+                     f"smooth ({iterations},{window})")
+
+
+def test_smoothing_bit_exact_full_blood_and_synthetic(blood_arrays):
+    _, y = blood_arrays
+    assert_bit_equal(gpu_smooth(y, 3, 3), O.smooth_values(y, 3, 3), "blood_01 (3,3)")
+    ys = synth.config3(1, n=32768)
+    assert_bit_equal(gpu_smooth(ys, 3, 3), O.smooth_values(ys, 3, 3), "synthetic f64 (3,3)")
+    yi = synth.config3(1, n=32768, integer=True)
+    assert_bit_equal(gpu_smooth(yi, 3, 3), O.smooth_values(yi, 3, 3), "synthetic int (3,3)")
+
+
+@pytest.mark.parametrize("n", [5, 6, 7, 8, 17, 63, 64, 65])
+def test_smoothing_short_inputs(n):
+    rng = np.random.default_rng(n)
+    y = rng.normal(0, 1000, n)
+    for it, w in [(3, 3), (2, 5), (3, 7), (1, 4)]:
+        assert_bit_equal(gpu_smooth(y, it, w), O.smooth_values(y, it, w), f"n={n} ({it},{w})")
+
+
+# ------------------------------------------------------------------------------ detection (K2/K3)
+def _check_detect(sm, what):
+    pk, sc = gpu_detect(sm)
+    d2 = O.second_derivative(sm)
+    want = O.detect_peaks(d2)
+    assert pk.shape[0] == want.shape[0], f"{what}: {pk.shape[0]} triplets vs {want.shape[0]}"
+    assert np.array_equal(pk.astype(np.int64), want.astype(np.int64)), f"{what}: triplets differ"
+    a = np.abs(d2)
+    want_sc = np.array([O.score_peak(a, int(l), int(c), int(r)) for l, c, r in want])
+    assert_bit_equal(sc, want_sc, f"{what}: scores")
+    return pk
+
+
+def test_detection_reference_kats():
+    # common.rs:50-58 / detector.rs:172-208, through the full detector on tiny inputs.
+    # [1,2,3,2,1] -> d2 = [0,-2,0]; centre 2; no borders inside -> NoPeaksDetected-style empty list
+    pk, _ = gpu_detect(np.array([1.0, 2.0, 3.0, 2.0, 1.0]))
+    assert pk.shape[0] == 0
+    # a bump wide enough to have both borders
+    y = np.array([0, 0, 1, 3, 7, 12, 15, 12, 7, 3, 1, 0, 0, 0.0])
+    _check_detect(y, "bump")
+
+
+def test_detection_bit_exact_blood(blood_arrays):
+    _, y = blood_arrays
+    sm = O.smooth_values(y, 3, 3)
+    pk = _check_detect(sm, "blood_01")
+    assert pk.shape[0] == 16100
+
+
+@pytest.mark.parametrize("seed,integer,n", [(0, False, 131072), (1, True, 65536), (2, False, 4099), (3, True, 1000)])
+def test_detection_bit_exact_synthetic(seed, integer, n):
+    y = synth.config3(seed, n=n, integer=integer)
+    _check_detect(O.smooth_values(y, 3, 3), f"synthetic seed={seed}")
+    _check_detect(y, f"synthetic unsmoothed seed={seed}")
+
+
+def test_detection_edge_inputs():
+    rng = np.random.default_rng(7)
+    for n in (5, 6, 7, 9, 31, 64, 65, 127, 129):
+        _check_detect(rng.normal(0, 1, n), f"noise n={n}")
+    _check_detect(np.zeros(1000), "zeros")
+    _check_detect(np.arange(1000, dtype=np.float64) ** 2, "parabola")
+    t = np.linspace(0, 40 * np.pi, 5000)
+    _check_detect(np.sin(t) * 1e6, "sine")          # smooth: long monotone d2 runs, far borders
+    _check_detect(np.rint(np.sin(t) * 50), "ties")  # exact ties in d2
+    y = rng.normal(0, 1, 3000)
+    y[100] = np.nan
+    _check_detect(y, "nan")
+
+
+# ------------------------------------------------------------------------------ selection (K4)
+def _check_select(dec, okind, thr, sm, sb_idx, ig, what):
+    st, pk, (mean, sd) = gpu_select(dec, sm, sb_idx, ig)
+    want = O.select_peaks(sm, okind, thr, sb_idx, ig)
+    assert st == want.status or (want.status == O.PANIC and st == 100), f"{what}: status {st} vs {want.status}"
+    if want.status != O.OK:
+        return
+    assert np.array_equal(pk.astype(np.int64), want.peaks.astype(np.int64)), f"{what}: selected peaks differ"
+    if okind == O.SELECT_NOISE_SCORE_FILTER:
+        assert_bit_equal([mean, sd], [want.mean, want.sd], f"{what}: mean/sd")
+
+
+def test_selection_blood(blood_arrays):
+    x, y = blood_arrays
+    sm = O.smooth_values(y, 3, 3)
+    sb_idx = O.signal_boundaries_indices(x, (11.8, -2.2))
+    ig = O.ignore_region_indices(x, (11.8, -2.2), [(4.7, 4.9)])
+    dec = Deconvoluter()
+    _check_select(dec, O.SELECT_NOISE_SCORE_FILTER, 5.0, sm, sb_idx, None, "blood no-ignore")
+    _check_select(dec, O.SELECT_NOISE_SCORE_FILTER, 5.0, sm, sb_idx, ig, "blood water ignored")
+    st, pk, (mean, sd) = gpu_select(dec, sm, sb_idx, ig)
+    assert pk.shape[0] == 981 and pk[0].tolist() == [41583, 41585, 41588] and pk[-1].tolist() == [97895, 97896, 97898]
+    assert float(mean).hex() == "0x1.1ac34b169a537p+8" and float(sd).hex() == "0x1.6a11671179e58p+7"  # Appendix B
+    for thr in (0.5, 6.4, 8.0, 1e6):
+        dec.set_noise_score_selector(thr)
+        _check_select(dec, O.SELECT_NOISE_SCORE_FILTER, thr, sm, sb_idx, ig, f"blood thr={thr}")
+    dec.set_detector_only()
+    _check_select(dec, O.SELECT_DETECTOR_ONLY, 0.0, sm, sb_idx, None, "blood detector-only")
+    _check_select(dec, O.SELECT_DETECTOR_ONLY, 0.0, sm, sb_idx, ig, "blood detector-only ignore")
+
+
+def test_selection_region_edge_cases(blood_arrays):
+    x, y = blood_arrays
+    sm = O.smooth_values(y, 3, 3)[:20000]
+    dec = Deconvoluter()
+    n = sm.size
+    cases = [(0, n), (0, 10), (n - 10, n), (5000, 5001), (5000, 5000), (19990, 20000), (3, 7), (100, 19000),
+             (19000, 100), (n + 5, n + 9)]
+    for sb in cases:
+        _check_select(dec, O.SELECT_NOISE_SCORE_FILTER, 5.0, sm, sb, None, f"sb={sb}")
+        _check_select(dec, O.SELECT_NOISE_SCORE_FILTER, 5.0, sm, sb, [(6000, 9000), (12000, 12001)], f"sb={sb} ig")
+    # everything ignored -> the reference panics
+    _check_select(dec, O.SELECT_NOISE_SCORE_FILTER, 5.0, sm, (100, 19000), [(0, n)], "all ignored")
+    # no peaks at all
+    st, _, _ = gpu_select(dec, np.zeros(500), (10, 400), None)
+    assert st == _lib.MDB_ERR_NO_PEAKS_DETECTED
+
+
+def test_selection_synthetic():
+    dec = Deconvoluter()
+    for seed, integer in [(0, False), (1, True), (2, False)]:
+        y = synth.config3(seed, n=65536, integer=integer)
+        x = synth.axis(65536)
+        sm = O.smooth_values(y, 3, 3)
+        sb_idx = O.signal_boundaries_indices(x, synth.SIGNAL_BOUNDARIES)
+        _check_select(dec, O.SELECT_NOISE_SCORE_FILTER, 5.0, sm, sb_idx, None, f"synthetic {seed}")
+
+
+# ------------------------------------------------------------------------------ fit (K5/K6)
+def test_fit_reference_kat():
+    # fitter_analytical.rs:188-196: stencil (4,5),(8,10),(12,5) -> maxp 8, hw 4, sfhw/hw 40.
+    # One peak, one iteration would rescale; use the trace's initial solve.
+    x = np.arange(0.0, 16.0, 1.0)
+    y = np.zeros(16)
+    y[4], y[8], y[12] = 5.0, 10.0, 5.0
+    _, tr = gpu_fit(x, y, [[4, 8, 12]], 1)
+    sfhw, hw2, maxp = tr[0, 0]
+    assert abs(maxp - 8.0) < 1e-12 and abs(np.sqrt(hw2) - 4.0) < 1e-12 and abs(sfhw / np.sqrt(hw2) - 40.0) < 1e-10
+    want, wtr = O.fit_lorentzian(x, y, [[4, 8, 12]], 1, trace=True)
+    assert_bit_equal(tr, wtr, "single-stencil trace")
+
+
+def test_fit_bit_exact_blood_every_iteration(blood_arrays):
+    x, y = blood_arrays
+    r = O.deconvolute_spectrum(O.Settings(ignore_regions=[(4.7, 4.9)]), x, y, (11.8, -2.2))
+    want, wtr = O.fit_lorentzian(x, y, r.peaks, 10, trace=True)
+    got, tr = gpu_fit(x, y, r.peaks, 10)
+    for it in range(11):
+        assert_bit_equal(tr[it], wtr[it], f"blood fit, state after pass {it}")
+    assert got.shape[0] == 760  # Appendix B
+    assert_bit_equal(got, want, "blood retained lorentzians")
+    assert float(got[0, 0]).hex() == "0x1.084fd4b50b8dfp-4" and float(got[0, 2]).hex() == "0x1.0eac0d0cd9679p+3"
+
+
+@pytest.mark.parametrize("iterations", [1, 2, 5, 15])
+def test_fit_bit_exact_synthetic(iterations):
+    n = 32768
+    x = synth.axis(n)
+    y = synth.config3(4, n=n)
+    r = O.deconvolute_spectrum(O.Settings(), x, y, synth.SIGNAL_BOUNDARIES)
+    assert r.status == O.OK and len(r.peaks) > 100
+    want, wtr = O.fit_lorentzian(x, y, r.peaks, iterations, trace=True)
+    got, tr = gpu_fit(x, y, r.peaks, iterations)
+    assert_bit_equal(tr, wtr, f"synthetic fit trace it={iterations}")
+    assert_bit_equal(got, want, "synthetic retained")
+
+
+def test_fit_many_peaks_tiles():
+    # more peaks than one shared-memory tile (FIT_TILE = 512) and a ragged last block
+    n = 131072
+    x = synth.axis(n)
+    y = synth.config5(0, n=n)
+    r = O.deconvolute_spectrum(O.Settings(), x, y, synth.SIGNAL_BOUNDARIES)
+    assert len(r.peaks) > 2000
+    want, wtr = O.fit_lorentzian(x, y, r.peaks, 3, trace=True)
+    got, tr = gpu_fit(x, y, r.peaks, 3)
+    assert_bit_equal(tr, wtr, "config-5 fit trace")
+    assert_bit_equal(got, want, "config-5 retained")
+
+
+# ------------------------------------------------------------------------------ end to end (a1)
+def _check_e2e(dec, osettings, spectra, what):
+    outs = dec.deconvolute_spectra(spectra)
+    for i, (sp, out) in enumerate(zip(spectra, outs)):
+        r = O.deconvolute_spectrum(osettings, sp.chemical_shifts, sp.intensities, sp.signal_boundaries)
+        assert r.status == O.OK
+        assert np.array_equal(out.peaks.astype(np.int64), r.peaks.astype(np.int64)), f"{what}[{i}]: peak set differs"
+        assert_bit_equal(out.parameters, r.lorentzians, f"{what}[{i}]: lorentzians")
+        assert_bit_equal([out.mse], [r.mse], f"{what}[{i}]: mse")
+    return outs
+
+
+def test_config1_blood_default_deconvoluter(golden_dir):
+    sp = Spectrum.read_bruker(os.path.join(golden_dir, "bruker", "blood_01"), 10, 10, (-2.2, 11.8))
+    dec = Deconvoluter()
+    dec.add_ignore_region((4.7, 4.9))
+    out = _check_e2e(dec, O.Settings(ignore_regions=[(4.7, 4.9)]), [sp], "blood_01 water ignored")[0]
+    assert len(out.lorentzians) == 760 and float(out.mse).hex() == "0x1.0808a64fe177ep+35"  # Appendix B
+    dec.clear_ignore_regions()
+    out = _check_e2e(dec, O.Settings(), [sp], "blood_01")[0]
+    assert out.peaks.shape[0] == 992 and len(out.lorentzians) == 766
+    # single-spectrum entry points agree with the batch one
+    one = dec.par_deconvolute_spectrum(sp)
+    assert_bit_equal(one.parameters, out.parameters, "par_deconvolute_spectrum")
+
+
+def test_sim_spectrum_recovers_generating_parameters(golden_dir):
+    # reference integration test `sim` (tests/deconvoluter.rs:7-21): sim_01, signal region 3.35..3.55
+    sp = Spectrum.read_bruker(os.path.join(golden_dir, "bruker", "sim_01"), 10, 10, (3.35, 3.55))
+    dec = Deconvoluter()
+    out = _check_e2e(dec, O.Settings(), [sp], "sim_01")[0]
+    truth = np.loadtxt(os.path.join(golden_dir, "bruker", "sim_01", "lorentzians.csv"), delimiter=",", skiprows=1)
+    # approximate known answer: every fitted maxp sits within two grid steps of a generating peak
+    step = abs(sp.chemical_shifts[1] - sp.chemical_shifts[0])
+    dist = np.min(np.abs(out.parameters[:, 2][:, None] - truth[:, 2][None, :]), axis=1)
+    assert np.median(dist) < 2 * step
+
+
+def test_batch_mixed_lengths_settings_and_order():
+    specs = []
+    for s, (n, integer) in enumerate([(32768, False), (16384, True), (32768, False), (20000, False), (8192, True)]):
+        x = synth.axis(n)
+        specs.append(Spectrum(x, synth.config3(10 + s, n=n, integer=integer, x=x), (-2.2, 11.8)))
+    dec = Deconvoluter()
+    _check_e2e(dec, O.Settings(), specs, "mixed batch default")
+    dec.set_moving_average_smoother(2, 5)
+    dec.set_noise_score_selector(6.5)
+    dec.set_analytical_fitter(5)
+    dec.add_ignore_region((4.7, 4.9))
+    _check_e2e(dec, O.Settings(smoothing_iterations=2, smoothing_window=5, threshold=6.5, fitting_iterations=5,
+                               ignore_regions=[(4.7, 4.9)]), specs, "mixed batch custom")
+    dec = Deconvoluter()
+    dec.set_identity_smoother()
+    _check_e2e(dec, O.Settings(smoothing_kind=O.SMOOTH_IDENTITY), specs[:2], "identity smoother")
+    dec = Deconvoluter()
+    dec.set_detector_only()
+    dec.set_analytical_fitter(2)
+    _check_e2e(dec, O.Settings(selection_kind=O.SELECT_DETECTOR_ONLY, fitting_iterations=2), specs[1:2], "detector only")
+
+
+def test_batch_spanning_several_chunks(monkeypatch):
+    monkeypatch.setenv("MDB_CHUNK_SPECTRA", "3")
+    n = 8192
+    x = synth.axis(n)
+    specs = [Spectrum(x, synth.config3(100 + s, n=n, x=x), (-2.2, 11.8)) for s in range(11)]
+    _check_e2e(Deconvoluter(), O.Settings(), specs, "11 spectra in chunks of 3")
+
+
+def test_error_semantics_first_failure_wins():
+    n = 4096
+    x = synth.axis(n)
+    good = Spectrum(x, synth.config3(5, n=n, x=x), (-2.2, 11.8))
+    flat = Spectrum(x, np.zeros(n), (-2.2, 11.8))                       # NoPeaksDetected
+    narrow = Spectrum(x, synth.config3(6, n=n, x=x), (5.0, 5.0 + 3 * abs(x[1] - x[0])))  # nothing selectable
+    dec = Deconvoluter()
+    with pytest.raises(exceptions.NoPeaksDetected):
+        dec.deconvolute_spectra([good, flat, narrow])
+    with pytest.raises(exceptions.EmptySignalRegion):
+        dec.deconvolute_spectra([good, narrow, flat])
+    r = O.deconvolute_spectrum(O.Settings(), narrow.chemical_shifts, narrow.intensities, narrow.signal_boundaries)
+    assert r.status == O.EMPTY_SIGNAL_REGION
+    assert len(dec.deconvolute_spectra([])) == 0
+
+
+def test_device_resident_inputs_match_host_inputs():
+    torch = pytest.importorskip("torch")
+    lib = _lib.load()
+    n = 16384
+    x = synth.axis(n)
+    ys = np.stack([synth.config3(40 + s, n=n, x=x) for s in range(4)])
+    dec = Deconvoluter()
+    host = dec.deconvolute_spectra([Spectrum(x, y, (-2.2, 11.8)) for y in ys])
+    xd = torch.from_numpy(x).cuda()
+    yd = torch.from_numpy(ys).cuda()
+    views = (_lib.SpectrumView * 4)()
+    for i in range(4):
+        views[i].chemical_shifts = xd.data_ptr()
+        views[i].intensities = yd[i].data_ptr()
+        views[i].len = n
+        views[i].signal_boundaries[0], views[i].signal_boundaries[1] = 11.8, -2.2
+    batch = C.c_void_p()
+    assert lib.mdb_deconvolute_spectra(dec._h, views, 4, _lib.MDB_MEM_DEVICE, C.byref(batch)) == 0, _lib.last_error()
+    try:
+        for i in range(4):
+            k = lib.mdb_batch_n_lorentzians(batch, i)
+            got = np.ctypeslib.as_array(C.cast(lib.mdb_batch_lorentzians(batch, i), C.POINTER(C.c_double)), (k, 3)).copy()
+            assert_bit_equal(got, host[i].parameters, f"device input {i}")
+            assert lib.mdb_batch_mse(batch, i) == host[i].mse
+    finally:
+        lib.mdb_batch_free(batch)
