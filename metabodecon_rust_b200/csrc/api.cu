@@ -7,6 +7,7 @@
 // Reference citations are relative to /root/reference/metabodecon/src/.
 #include "../../include/mdb200.h"
 #include "kernels.cuh"
+#include "smooth_fast.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -604,6 +605,36 @@ static int smem_optin_limit()
     return lim;
 }
 
+// K1 dispatch: the pipelined TMA-staged kernel when the settings are covered (odd window 3/5/7,
+// 1..10 iterations) and every input row is 16-byte aligned, else one generic pass per launch.
+static mdb_status launch_smooth(cudaStream_t stream, const SpecDesc *d_desc, const std::vector<SpecDesc> &descs,
+                                int iters, int window, std::vector<ProfSpan> *spans)
+{
+    const size_t S = descs.size();
+    double pts = 0.0;
+    bool aligned = true;
+    for (const SpecDesc &d : descs) {
+        pts += (double)d.n;
+        aligned = aligned && (((uintptr_t)d.y & 15) == 0) && (((uintptr_t)d.ys & 15) == 0);
+    }
+    size_t smem = 0;
+    SmoothFastFn fn = smooth_fast_lookup(window, iters, &smem);
+    const char *force = std::getenv("MDB_SMOOTH_GENERIC");
+    prof_begin(spans, MDB_KERNEL_SMOOTH, stream);
+    if (fn && aligned && !(force && force[0] == '1')) {
+        CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        fn<<<(unsigned)((S + 31) / 32), SM_THREADS, smem, stream>>>(d_desc, (int)S);
+        LAUNCH_CHECK();
+    } else {
+        for (int p = 0; p < iters; ++p) {
+            smooth_pass_generic_kernel<<<(unsigned)((S + 31) / 32), 32, 0, stream>>>(d_desc, (int)S, p, iters, window);
+            LAUNCH_CHECK();
+        }
+    }
+    prof_end(spans, stream, 16.0 * pts);  // algorithmic bytes: read 8N + write 8N
+    return MDB_OK;
+}
+
 // Stage A: inputs -> device, smoothing, detection, selection, counts back to the host.
 static mdb_status stage_a(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_deconvoluter &dc, int memory,
                           bool skip_smoothing_input_is_smoothed)
@@ -726,15 +757,9 @@ static mdb_status stage_a(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
     // ---- K1 smoothing (deconvoluter.rs:531-532)
     if (!skip_smoothing_input_is_smoothed) {
         if (ma) {
-            const int iters = (int)dc.smoothing.iterations, window = (int)dc.smoothing.window_size;
-            double pts = 0.0;
-            for (size_t s = 0; s < S; ++s) pts += (double)ck.desc[s].n;
-            prof_begin(&ck.spans, MDB_KERNEL_SMOOTH, ws.stream);
-            for (int p = 0; p < iters; ++p) {
-                smooth_pass_generic_kernel<<<(unsigned)((S + 31) / 32), 32, 0, ws.stream>>>(d_desc, (int)S, p, iters, window);
-                LAUNCH_CHECK();
-            }
-            prof_end(&ck.spans, ws.stream, 16.0 * pts);  // algorithmic bytes: read 8N + write 8N
+            mdb_status sst = launch_smooth(ws.stream, d_desc, ck.desc, (int)dc.smoothing.iterations,
+                                           (int)dc.smoothing.window_size, &ck.spans);
+            if (sst != MDB_OK) return sst;
         } else {  // Identity (smoothing/identity.rs): the smoothed copy is the input itself
             for (size_t s = 0; s < S; ++s)
                 CUDA_TRY(cudaMemcpyAsync(ck.desc[s].ys, ck.desc[s].y, (size_t)ck.desc[s].n * 8,
@@ -1025,7 +1050,10 @@ extern "C" mdb_status mdb_deconvolute_spectra(const mdb_deconvoluter *d, const m
     // counts of chunk k, and chunk k-1 is unpacked while chunk k runs its fit / MSE kernels.
     const size_t csz = chunk_size_for(hs);
     const size_t n_chunks = (n_spectra + csz - 1) / csz;
-    const size_t n_ws = std::min<size_t>(3, n_chunks);
+    size_t depth = 3;
+    if (const char *env = std::getenv("MDB_PIPELINE_DEPTH"))
+        if (std::atoi(env) >= 1) depth = (size_t)std::min(std::atoi(env), 8);
+    const size_t n_ws = std::min<size_t>(depth, n_chunks);
     std::vector<Workspace *> wss(n_ws, nullptr);
     auto cleanup = [&]() {
         for (Workspace *w : wss)
@@ -1041,14 +1069,21 @@ extern "C" mdb_status mdb_deconvolute_spectra(const mdb_deconvoluter *d, const m
     }
     st = stage_a(chunks[0], hs, *d, memory, false);
     for (size_t k = 0; st == MDB_OK && k < n_chunks; ++k) {
+        if (n_ws == 1) {  // strictly serial (used for per-kernel profiling): A(k) B(k) finish(k) A(k+1)
+            st = stage_b(chunks[k], hs, *d, batch->r, true, nullptr);
+            if (st == MDB_OK) st = finish_chunk(chunks[k], batch->r, true);
+            if (st == MDB_OK && k + 1 < n_chunks) st = stage_a(chunks[k + 1], hs, *d, memory, false);
+            continue;
+        }
         if (k + 1 < n_chunks) {
             if (k + 1 >= n_ws) st = finish_chunk(chunks[k + 1 - n_ws], batch->r, true);  // frees that workspace
             if (st == MDB_OK) st = stage_a(chunks[k + 1], hs, *d, memory, false);
         }
         if (st == MDB_OK) st = stage_b(chunks[k], hs, *d, batch->r, true, nullptr);
     }
-    for (size_t k = (n_chunks >= n_ws ? n_chunks - n_ws : 0); st == MDB_OK && k < n_chunks; ++k)
-        if (chunks[k].stage_b_launched) st = finish_chunk(chunks[k], batch->r, true);
+    if (n_ws > 1)
+        for (size_t k = (n_chunks >= n_ws ? n_chunks - n_ws : 0); st == MDB_OK && k < n_chunks; ++k)
+            if (chunks[k].stage_b_launched) st = finish_chunk(chunks[k], batch->r, true);
     cleanup();
     if (st != MDB_OK) return st;
     mdb_status first = MDB_OK;
@@ -1130,9 +1165,10 @@ extern "C" mdb_status mdb_stage_smooth(const double *values, size_t n, uint64_t 
     d.n = (int)n;
     CUDA_TRY(cudaMemcpyAsync(ws->y.p, values, n * 8, cudaMemcpyHostToDevice, ws->stream));
     CUDA_TRY(cudaMemcpyAsync(ws->desc.p, &d, sizeof(d), cudaMemcpyHostToDevice, ws->stream));
-    for (int p = 0; p < (int)iterations; ++p) {
-        smooth_pass_generic_kernel<<<1, 32, 0, ws->stream>>>(ws->desc.as<SpecDesc>(), 1, p, (int)iterations, (int)window);
-        LAUNCH_CHECK();
+    {
+        std::vector<SpecDesc> descs(1, d);
+        if ((st = launch_smooth(ws->stream, ws->desc.as<SpecDesc>(), descs, (int)iterations, (int)window, nullptr)) != MDB_OK)
+            return st;
     }
     CUDA_TRY(cudaMemcpyAsync(out, ws->ys.p, n * 8, cudaMemcpyDeviceToHost, ws->stream));
     CUDA_TRY(cudaStreamSynchronize(ws->stream));

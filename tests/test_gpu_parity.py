@@ -160,6 +160,20 @@ def test_smoothing_bit_exact_full_blood_and_synthetic(blood_arrays):
     assert_bit_equal(gpu_smooth(yi, 3, 3), O.smooth_values(yi, 3, 3), "synthetic int (3,3)")
 
 
+@pytest.mark.parametrize("n,iterations,window", [(960, 3, 3), (9600, 3, 3), (96 * 7 + 1, 3, 3), (96 * 7 - 1, 2, 3),
+                                                 (800, 2, 5), (80 * 11, 9, 5), (840, 10, 7), (84 * 5, 4, 7),
+                                                 (192, 3, 3), (97, 3, 3), (288, 10, 3)])
+def test_smoothing_tile_boundaries(n, iterations, window):
+    # lengths that are exact multiples of the kernel's tile (96 / 80 / 84 points) or one off
+    rng = np.random.default_rng(n + iterations)
+    y = np.rint(rng.normal(0, 1e5, n))
+    assert_bit_equal(gpu_smooth(y, iterations, window), O.smooth_values(y, iterations, window),
+                     f"n={n} ({iterations},{window})")
+    y = rng.normal(0, 1e5, n)
+    assert_bit_equal(gpu_smooth(y, iterations, window), O.smooth_values(y, iterations, window),
+                     f"n={n} ({iterations},{window}) f64")
+
+
 @pytest.mark.parametrize("n", [5, 6, 7, 8, 17, 63, 64, 65])
 def test_smoothing_short_inputs(n):
     rng = np.random.default_rng(n)
