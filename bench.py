@@ -118,7 +118,7 @@ def run_reference(args, rank, world):
     import oracle as O
     k_true, hw_range, desc = WORKLOADS[args.workload]
     cores = O.max_threads()
-    n_sample = args.cpu_sample or max(8, 2 * cores)
+    n_sample = args.cpu_sample or 4 * cores
     x = axis(N_POINTS)
     ys = np.empty((n_sample, N_POINTS))
     for s in range(n_sample):
@@ -159,7 +159,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config5", choices=sorted(WORKLOADS))
     ap.add_argument("--spectra", type=int, default=2000, help="spectra per GPU per step")
-    ap.add_argument("--cpu-sample", type=int, default=0, help="spectra in the CPU baseline sample (0 = 2 x cores)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="spectra in the CPU baseline sample (0 = 16 x cores)")
+    ap.add_argument("--no-superposition", action="store_true", help="skip the config-4 superposition_vec measurement")
+    ap.add_argument("--sup-points", type=int, default=1 << 24, help="config 4: grid points (whole job, sharded over the GPUs)")
+    ap.add_argument("--sup-lorentzians", type=int, default=20000, help="config 4: Lorentzians")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -254,17 +257,24 @@ def main():
             ms = float(t.item())
         return ms, launches
 
-    # ---- value: inputs resident in HBM
+    # ---- value: inputs resident in HBM, three chunk pipelines in flight (the product's default)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ms_dev, launches = timed(dev_views, _lib.MDB_MEM_DEVICE, args.warmup, args.steps, profile=True)
+    ms_dev, launches = timed(dev_views, _lib.MDB_MEM_DEVICE, args.warmup, args.steps)
     clocks = sampler.stop()
+    value = world * S / (ms_dev / 1e3)
+
+    # ---- per-kernel rooflines: one extra step with the chunk pipeline forced serial
+    # (MDB_PIPELINE_DEPTH=1), so that every kernel is alone on the GPU while its CUDA events
+    # (recorded on the launching stream inside the library, mdb_profile_*) bracket it
+    os.environ["MDB_PIPELINE_DEPTH"] = "1"
+    ms_serial, _ = timed(dev_views, _lib.MDB_MEM_DEVICE, 1, 1, profile=True)
+    del os.environ["MDB_PIPELINE_DEPTH"]
     prof = {}
     for kid, name in enumerate(_lib.KERNEL_NAMES):
         ms, n, work = C.c_double(), C.c_uint64(), C.c_double()
         lib.mdb_profile_read(kid, C.byref(ms), C.byref(n), C.byref(work))
         prof[name] = {"ms": ms.value, "launches": int(n.value), "work": work.value}
-    value = world * S / (ms_dev / 1e3)
 
     # ---- e2e: host (pinned) buffers through the C ABI, copies inside the timed region
     e2e = None
@@ -275,10 +285,47 @@ def main():
         torch.cuda.synchronize()
         host_views = make_views(x_host.data_ptr(), y_host.data_ptr())
         ms_host, _ = timed(host_views, _lib.MDB_MEM_HOST, max(1, args.warmup), args.steps)
-        h2d = S * N_POINTS * 8 + N_POINTS * 8 * max(1, (S + 242) // 243)  # intensities + the axis once per chunk
+        chunk_max = min(512, (1536 << 20) // (48 * N_POINTS + 4096))  # chunk_size_for() in csrc/api.cu
+        h2d = S * N_POINTS * 8 + N_POINTS * 8 * ((S + chunk_max - 1) // chunk_max)  # intensities + the axis once per chunk
         d2h = stats["lorentzians"] * 24 + stats["peaks"] * 12 + S * (8 + 4 + 48)
         e2e = {"value": world * S / (ms_host / 1e3), "unit": "spectra/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_host, "host_memory": "pinned"}
+
+    # ---- config 4: one superposition_vec over a 2^24-point grid x 20,000 Lorentzians, the grid
+    # sharded contiguously over the ranks (strong scaling), parameters replicated, no exchange
+    sup = None
+    if not args.no_superposition:
+        n_all, p4 = args.sup_points, args.sup_lorentzians
+        lo, hi = rank * n_all // world, (rank + 1) * n_all // world
+        rng4 = np.random.Generator(np.random.PCG64(20260004))
+        maxp4 = rng4.uniform(0.0, 10.0, p4)
+        hw4 = np.exp(rng4.uniform(np.log(5e-4), np.log(3e-3), p4))
+        sf4 = np.exp(rng4.uniform(0.0, np.log(1e4), p4))
+        lor4 = torch.from_numpy(np.ascontiguousarray(np.stack([sf4 * hw4, hw4 * hw4, maxp4], axis=1))).to(dev)
+        x4 = torch.linspace(-2.2, 11.8, n_all, dtype=torch.float64)[lo:hi].contiguous().to(dev)
+        out4 = torch.empty_like(x4)
+
+        def sup_step():
+            st = lib.mdb_superposition_vec(x4.data_ptr(), hi - lo, lor4.data_ptr(), p4, out4.data_ptr(), _lib.MDB_MEM_DEVICE)
+            assert st == 0, _lib.last_error()
+
+        sup_step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(2):
+            sup_step()
+        e1.record()
+        barrier()
+        ms4 = e0.elapsed_time(e1) / 2
+        if world > 1:
+            t = torch.tensor([ms4], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms4 = float(t.item())
+        sup = {"workload": f"config4: superposition_vec, {n_all} grid points x {p4} Lorentzians, grid sharded over {world} GPU(s)",
+               "evals_per_s": n_all * p4 / (ms4 / 1e3), "ms": ms4, "scaling": "strong",
+               "checksum": float(out4[:: max(1, (hi - lo) // 1024)].sum().item())}
+        del x4, out4
 
     if rank != 0:
         if world > 1:
@@ -320,6 +367,9 @@ def main():
                 "bytes_per_launch": p["work"] / p["launches"], "ms_per_launch": p["ms"] / p["launches"],
                 "launches": p["launches"]}
 
+    if sup is not None:
+        sup["fp64_pipe_util"] = sup["evals_per_s"] * FP64_INSTR_PER_EVAL / (world * N_SM * FP64_LANES_PER_SM * sm_mhz * 1e6)
+        sup["frac_of_fp64_peak"] = sup["evals_per_s"] * FLOPS_PER_EVAL / 1e12 / (world * fp64_peak_tflops)
     dominant = max(("mse_superposition", "fit_iter"), key=lambda k: prof[k]["ms"])
     roofline = fp64_roofline(dominant)
     other = fp64_roofline("fit_iter" if dominant == "mse_superposition" else "mse_superposition")
@@ -330,7 +380,7 @@ def main():
     if not args.no_cpu_baseline and world == 1:
         import oracle as O
         cores = O.max_threads()
-        n_sample = min(S, args.cpu_sample or max(8, 2 * cores))
+        n_sample = min(S, args.cpu_sample or 16 * cores)
         ys = y_dev[:n_sample].cpu().numpy()
         O.par_deconvolute_spectra(O.Settings(), x_np, ys[:min(n_sample, cores)], SB)  # warm-up
         t0 = time.perf_counter()
@@ -362,7 +412,9 @@ def main():
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "roofline": roofline, "roofline_other_fp64": other,
         "roofline_hbm": {"detect": hbm_roofline("detect"), "smooth": hbm_roofline("smooth")},
-        "kernel_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items() if v["launches"]},
+        "kernel_ms_serial_step": {k: v["ms"] for k, v in prof.items() if v["launches"]},
+        "serial_step_ms": ms_serial,
+        "superposition_vec": sup,
         "cpu_baseline": cpu, "parity_sample": parity,
     }
     print(json.dumps(line), flush=True)

@@ -605,6 +605,18 @@ static int smem_optin_limit()
     return lim;
 }
 
+static int sm_count()
+{
+    static int n = -1;
+    if (n < 0) {
+        int dev = 0, v = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        n = v > 0 ? v : 148;
+    }
+    return n;
+}
+
 // K1 dispatch: the pipelined TMA-staged kernel when the settings are covered (odd window 3/5/7,
 // 1..10 iterations) and every input row is 16-byte aligned, else one generic pass per launch.
 static mdb_status launch_smooth(cudaStream_t stream, const SpecDesc *d_desc, const std::vector<SpecDesc> &descs,
@@ -840,7 +852,7 @@ static mdb_status stage_b(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
                 ++f.seg_cnt;
             }
         }
-        ck.p_total += f.n_peaks;
+        ck.p_total += (f.n_peaks + 1) & ~1;  // even offsets: every parameter block stays 16-byte aligned (TMA bulk copies)
         ck.max_peaks = std::max(ck.max_peaks, f.n_peaks);
     }
     const size_t P = (size_t)std::max<long long>(ck.p_total, 1);
@@ -881,17 +893,19 @@ static mdb_status stage_b(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
         prof_end(&ck.spans, ws.stream, (double)ck.p_total);
         double evals_per_pass = 0.0;  // E_fit per pass = 3 * P_s^2
         for (size_t s = 0; s < S; ++s) evals_per_pass += 3.0 * (double)ck.fdesc[s].n_peaks * (double)ck.fdesc[s].n_peaks;
+        // trace is a single-spectrum facility (mdb_stage_fit): p_total carries alignment padding, n_peaks does not
+        const size_t n_trace = (size_t)ck.fdesc[0].n_peaks;
         if (trace) {
-            CUDA_TRY(cudaMemcpyAsync(trace, st.pa, (size_t)ck.p_total * 24, cudaMemcpyDeviceToHost, ws.stream));
+            CUDA_TRY(cudaMemcpyAsync(trace, st.pa, n_trace * 24, cudaMemcpyDeviceToHost, ws.stream));
         }
         double *pin = st.pa, *pout = st.pb;
         for (int it = 0; it < iters; ++it) {
             prof_begin(&ck.spans, MDB_KERNEL_FIT_ITER, ws.stream);
-            fit_iter_kernel<<<grid, FIT_THREADS, 0, ws.stream>>>(d_fd, st, pin, pout);
+            fit_iter_kernel<<<grid, FIT_THREADS, LOR_SMEM_BYTES, ws.stream>>>(d_fd, st, pin, pout);
             LAUNCH_CHECK();
             prof_end(&ck.spans, ws.stream, evals_per_pass);
             if (trace)
-                CUDA_TRY(cudaMemcpyAsync(trace + (size_t)(it + 1) * ck.p_total, pout, (size_t)ck.p_total * 24,
+                CUDA_TRY(cudaMemcpyAsync(trace + (size_t)(it + 1) * n_trace, pout, n_trace * 24,
                                          cudaMemcpyDeviceToHost, ws.stream));
             std::swap(pin, pout);
         }
@@ -902,13 +916,18 @@ static mdb_status stage_b(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
     LAUNCH_CHECK();
     prof_end(&ck.spans, ws.stream, (double)ck.p_total);
     if (with_mse && n_seg) {
-        const int per_block = SUP_THREADS * SUP_R;
+        // R = 8 points per thread is the throughput shape; small batches use R = 2 to fill the SMs
+        long long blocks8 = 0;
+        for (const Segment &sg : ck.segs) blocks8 += (sg.end - sg.start + SUP_THREADS * 8 - 1) / (SUP_THREADS * 8);
+        const int r = blocks8 >= 2 * sm_count() ? 8 : 2;
+        const int per_block = SUP_THREADS * r;
         dim3 grid((unsigned)((ck.max_seg_len + per_block - 1) / per_block), (unsigned)n_seg);
         if (grid.x > 0) {
             prof_begin(&ck.spans, MDB_KERNEL_MSE_SUPERPOSITION, ws.stream);
-            superposition_kernel<1><<<grid, SUP_THREADS, 0, ws.stream>>>(
-                nullptr, 0, nullptr, 0, ws.resid.as<double>(), d_desc, d_fd, ws.segs.as<Segment>(),
-                ws.lor.as<double>(), ws.n_kept.as<int>());
+            auto kern = r == 8 ? superposition_kernel<1, 8> : superposition_kernel<1, 2>;
+            kern<<<grid, SUP_THREADS, LOR_SMEM_BYTES, ws.stream>>>(nullptr, 0, nullptr, 0, ws.resid.as<double>(), d_desc, d_fd,
+                                                                  ws.segs.as<Segment>(), ws.lor.as<double>(),
+                                                                  ws.n_kept.as<int>());
             LAUNCH_CHECK();
             prof_end(&ck.spans, ws.stream, -1.0);  // work = sum(points * kept), known in finish_chunk
         }
@@ -1048,8 +1067,9 @@ extern "C" mdb_status mdb_deconvolute_spectra(const mdb_deconvoluter *d, const m
 
     // Three workspaces in flight: stage A of chunk k+1 is queued before the host waits for the
     // counts of chunk k, and chunk k-1 is unpacked while chunk k runs its fit / MSE kernels.
-    const size_t csz = chunk_size_for(hs);
-    const size_t n_chunks = (n_spectra + csz - 1) / csz;
+    const size_t csz_max = chunk_size_for(hs);
+    const size_t n_chunks = (n_spectra + csz_max - 1) / csz_max;
+    const size_t csz = (n_spectra + n_chunks - 1) / n_chunks;  // equal-sized chunks, no straggler
     size_t depth = 3;
     if (const char *env = std::getenv("MDB_PIPELINE_DEPTH"))
         if (std::atoi(env) >= 1) depth = (size_t)std::min(std::atoi(env), 8);
@@ -1116,20 +1136,25 @@ extern "C" mdb_status mdb_superposition_vec(const double *x, size_t n, const mdb
     if (memory == MDB_MEM_HOST) {
         CUDA_TRY(ws->x.ensure(n * 8));
         CUDA_TRY(ws->ys.ensure(n * 8));
-        CUDA_TRY(ws->lor.ensure(std::max<size_t>(p, 1) * 24));
         CUDA_TRY(cudaMemcpyAsync(ws->x.p, x, n * 8, cudaMemcpyHostToDevice, ws->stream));
-        if (p) CUDA_TRY(cudaMemcpyAsync(ws->lor.p, lor, p * 24, cudaMemcpyHostToDevice, ws->stream));
         dx = ws->x.as<double>();
-        dl = ws->lor.as<double>();
         dout = ws->ys.as<double>();
     }
-    const size_t per_block = (size_t)SUP_THREADS * SUP_R;
+    if (memory == MDB_MEM_HOST || ((uintptr_t)lor & 15) != 0) {  // the kernel's bulk copies need 16-byte alignment
+        CUDA_TRY(ws->lor.ensure(std::max<size_t>(p, 1) * 24));
+        if (p) CUDA_TRY(cudaMemcpyAsync(ws->lor.p, lor, p * 24, memory == MDB_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, ws->stream));
+        dl = ws->lor.as<double>();
+    }
+    const size_t blocks8 = (n + (size_t)SUP_THREADS * 8 - 1) / ((size_t)SUP_THREADS * 8);
+    const int r = blocks8 >= (size_t)2 * sm_count() ? 8 : 2;
+    const size_t per_block = (size_t)SUP_THREADS * r;
     const size_t blocks = (n + per_block - 1) / per_block;
     if (blocks > 0x7fffffffull) return fail(MDB_ERR_INVALID_ARGUMENT, "grid too large");
     std::vector<ProfSpan> spans;
     prof_begin(&spans, MDB_KERNEL_SUPERPOSITION_VEC, ws->stream);
-    superposition_kernel<0><<<(unsigned)blocks, SUP_THREADS, 0, ws->stream>>>(dx, (long long)n, dl, (int)p, dout, nullptr,
-                                                                             nullptr, nullptr, nullptr, nullptr);
+    auto kern = r == 8 ? superposition_kernel<0, 8> : superposition_kernel<0, 2>;
+    kern<<<(unsigned)blocks, SUP_THREADS, LOR_SMEM_BYTES, ws->stream>>>(dx, (long long)n, dl, (int)p, dout, nullptr, nullptr,
+                                                                      nullptr, nullptr, nullptr);
     LAUNCH_CHECK();
     prof_end(&spans, ws->stream, (double)n * (double)p);
     if (memory == MDB_MEM_HOST) CUDA_TRY(cudaMemcpyAsync(out, dout, n * 8, cudaMemcpyDeviceToHost, ws->stream));

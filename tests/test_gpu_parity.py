@@ -142,6 +142,80 @@ def test_superposition_empty_and_special_values():
         assert_bit_equal(superposition_vec_array(x, lor[k:k + 1]), O.superposition_vec(x, lor[k:k + 1]), f"special {k}")
 
 
+def _random_lorentzians(rng, p):
+    hw = np.exp(rng.uniform(np.log(5e-4), np.log(3e-3), p))
+    sf = np.exp(rng.uniform(0, np.log(1e4), p))
+    return np.stack([sf * hw, hw * hw, rng.uniform(0, 10, p)], axis=1)
+
+
+@pytest.mark.parametrize("n,p", [(303104, 33), (303105, 513), (400001, 1025), (131072, 1537), (1 << 20, 511)])
+def test_superposition_throughput_shape_and_tile_edges(n, p):
+    """n >= 2*148*1024 selects the 8-points-per-thread kernel; p around multiples of the 512-entry
+    TMA tile (odd p leaves a trailing 8 bytes that is copied by hand)."""
+    from metabodecon_rust_b200.lorentzian import superposition_vec_array
+    rng = np.random.default_rng(n + p)
+    x = rng.uniform(-2.2, 11.8, n)
+    lor = _random_lorentzians(rng, p)
+    assert_bit_equal(superposition_vec_array(x, lor), O.superposition_vec(x, lor, parallel=True), f"n={n} p={p}")
+
+
+@pytest.mark.parametrize("bad", [
+    [0.0, 1e-6, 5.0],            # sfhw == 0: quotient 0, outside the fast domain
+    [-3.0, 2e-7, 4.0],           # negative sfhw stays inside it
+    [1e-320, 1e-6, 5.0],         # denormal numerator
+    [1.0, 0.0, 5.0],             # hw2 == 0 (division by zero at x == maxp)
+    [1.0, -1e-6, 5.0],           # negative hw2
+    [1.0, 1e-310, 5.0],          # denormal hw2
+    [1e305, 1e-6, 5.0],          # huge numerator
+    [1.0, 1e-6, 1e200],          # (x - maxp)^2 overflows
+    [np.inf, 1e-6, 5.0], [1.0, np.inf, 5.0], [1.0, 1e-6, np.nan], [np.nan, 1e-6, 5.0],
+])
+def test_division_fast_and_ieee_paths_agree_with_oracle(bad):
+    """A tile whose parameters leave the fast domain must run the IEEE division loop; tiles before
+    and after it keep the fast path.  Either way the result is the oracle's, bit for bit."""
+    from metabodecon_rust_b200.lorentzian import superposition_vec_array
+    rng = np.random.default_rng(7)
+    lor = _random_lorentzians(rng, 1300)  # three tiles
+    x = np.concatenate([rng.uniform(-2.2, 11.8, 4000), [5.0, 4.0, 0.0]])
+    for pos in (0, 700, 1299):
+        cur = lor.copy()
+        cur[pos] = bad
+        got = superposition_vec_array(x, cur)
+        want = O.superposition_vec(x, cur)
+        both_nan = np.isnan(got) & np.isnan(want)  # NaN payloads are not part of the contract
+        assert_bit_equal(np.where(both_nan, 0.0, got), np.where(both_nan, 0.0, want), f"bad={bad} at {pos}")
+
+
+def test_division_fast_path_out_of_domain_x():
+    from metabodecon_rust_b200.lorentzian import superposition_vec_array
+    rng = np.random.default_rng(8)
+    lor = _random_lorentzians(rng, 600)
+    x = np.array([1e300, -1e155, 1e-320, 0.0, np.inf, np.nan, 3.3] + list(rng.uniform(0, 10, 300)))
+    got = superposition_vec_array(x, lor)
+    want = O.superposition_vec(x, lor)
+    both_nan = np.isnan(got) & np.isnan(want)
+    assert_bit_equal(np.where(both_nan, 0.0, got), np.where(both_nan, 0.0, want), "out-of-domain x")
+
+
+def test_superposition_device_memory_and_unaligned_parameters():
+    torch = pytest.importorskip("torch")
+    lib = _lib.load()
+    rng = np.random.default_rng(9)
+    n, p = 5000, 777
+    x = rng.uniform(-2.2, 11.8, n)
+    lor = _random_lorentzians(rng, p)
+    want = O.superposition_vec(x, lor)
+    dx = torch.from_numpy(x).cuda()
+    flat = torch.zeros(3 * p + 1, dtype=torch.float64, device="cuda")
+    for shift in (0, 1):  # shift 1: parameter block only 8-byte aligned
+        flat[shift:shift + 3 * p] = torch.from_numpy(lor.reshape(-1)).cuda()
+        out = torch.empty(n, dtype=torch.float64, device="cuda")
+        st = lib.mdb_superposition_vec(dx.data_ptr(), n, flat.data_ptr() + 8 * shift, p, out.data_ptr(), _lib.MDB_MEM_DEVICE)
+        assert st == 0, _lib.last_error()
+        torch.cuda.synchronize()
+        assert_bit_equal(out.cpu().numpy(), want, f"device memory, shift {shift}")
+
+
 # ------------------------------------------------------------------------------ smoothing (K1)
 @pytest.mark.parametrize("iterations,window", [(3, 3), (1, 3), (2, 5), (10, 7), (3, 4), (2, 2), (4, 9), (1, 65)])
 def test_smoothing_bit_exact_blood(blood_arrays, iterations, window):
