@@ -128,6 +128,41 @@ def test_bruker_reader_matches_reference_checks(golden_dir):
     assert len(sim) == 2048
 
 
+def test_jcampdx_reader_matches_bruker_reader(golden_dir):
+    """tests/parsing.rs:7-63 of the reference: the Bruker and JCAMP-DX forms of blood_01 agree
+    (intensities exactly -- both are the same int32 samples; chemical shifts to 1e-3)."""
+    from metabodecon_rust_b200.readers import read_bruker_arrays, read_jcampdx_arrays
+    xb, yb, _ = read_bruker_arrays(os.path.join(golden_dir, "bruker", "blood_01"), 10, 10)
+    xj, yj, meta = read_jcampdx_arrays(os.path.join(golden_dir, "jcampdx", "blood_01.dx"))
+    assert xj.size == yj.size == 131072
+    assert np.array_equal(yb, yj)
+    assert np.max(np.abs(xb - xj)) < 1e-3
+    assert xj[0] == 14.81146 and meta["nucleus"] == "1H" and abs(meta["frequency"] - 600.252821089118) < 1e-9
+
+
+def test_jcampdx_asdf_forms_decode_to_the_same_ordinates(tmp_path):
+    """The same ten ordinates written as AFFN, PAC, SQZ, DIF (with Y-checks) and DIFDUP
+    (JCAMP-DX 5.01 section 5.9 example style) must decode identically."""
+    from metabodecon_rust_b200.readers import read_jcampdx_arrays
+    want = [1000.0, 1001.0, 1003.0, 1003.0, 1003.0, 1003.0, 998.0, 990.0, 990.0, 1200.0]
+    header = ("##TITLE=t\n##JCAMP-DX=5.01\n##DATA TYPE=NMR SPECTRUM\n##DATA CLASS=XYDATA\n"
+              "##.OBSERVE FREQUENCY=600.0\n##.OBSERVE NUCLEUS=^1H\n##XUNITS=PPM\n##YUNITS=ARBITRARY UNITS\n"
+              "##XFACTOR=1\n##YFACTOR=1\n##FIRSTX=9\n##LASTX=0\n##NPOINTS=10\n##XYDATA=(X++(Y..Y))\n")
+    tables = {
+        "affn": "9 1000 1001 1003 1003 1003\n4 1003 998 990 990 1200\n",
+        "pac": "9+1000+1001+1003+1003+1003\n4+1003+998+990+990+1200\n",
+        "sqz": "9A000A001A003A003A003\n4A003I98I90I90A200\n",
+        "dif": "9A000JK%%\n5A003%n\n3I98q%\n1I90K10\n0A200\n",
+        "difdup": "9A000JK%T\n5A003%n\n3I98q%\n1I90K10\n0A200\n",
+    }
+    for name, table in tables.items():
+        path = tmp_path / f"{name}.dx"
+        path.write_text(header + table + "##END=\n")
+        x, y, _ = read_jcampdx_arrays(str(path))
+        assert y.tolist() == want, name
+        assert x[0] == 9.0 and x[-1] == 0.0
+
+
 @pytest.mark.skipif(_lib.load().mdb_device_count() > 0, reason="only meaningful without a GPU")
 def test_compute_fails_loudly_without_a_device():
     x = np.linspace(10.0, 0.0, 100)

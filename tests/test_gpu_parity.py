@@ -443,6 +443,21 @@ def test_config1_blood_default_deconvoluter(golden_dir):
     assert_bit_equal(one.parameters, out.parameters, "par_deconvolute_spectrum")
 
 
+def test_config2_jcampdx_blood_default_deconvoluter(golden_dir):
+    """BASELINE config 2: the bundled JCAMP-DX spectrum (XYDATA, DIFDUP) with default settings.
+    Its axis differs from the Bruker one at the 1e-4 ppm level (Hz grid + .SHIFT REFERENCE), so the
+    result is compared with the oracle run on the same decoded arrays."""
+    sp = Spectrum.read_jcampdx(os.path.join(golden_dir, "jcampdx", "blood_01.dx"), (-2.2, 11.8))
+    assert len(sp) == 131072
+    out = _check_e2e(Deconvoluter(), O.Settings(), [sp], "blood_01.dx")[0]
+    assert out.peaks.shape[0] > 900 and len(out.lorentzians) > 700
+    # same intensities as config 1; the axes drift apart by up to one grid step over the range, so
+    # the signal-boundary indices (and with them the noise threshold) may differ by one point
+    bru = Spectrum.read_bruker(os.path.join(golden_dir, "bruker", "blood_01"), 10, 10, (-2.2, 11.8))
+    ref = Deconvoluter().deconvolute_spectrum(bru)
+    assert abs(out.peaks.shape[0] - ref.peaks.shape[0]) <= 0.02 * ref.peaks.shape[0]
+
+
 def test_sim_spectrum_recovers_generating_parameters(golden_dir):
     # reference integration test `sim` (tests/deconvoluter.rs:7-21): sim_01, signal region 3.35..3.55
     sp = Spectrum.read_bruker(os.path.join(golden_dir, "bruker", "sim_01"), 10, 10, (3.35, 3.55))
