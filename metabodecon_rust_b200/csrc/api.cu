@@ -7,7 +7,7 @@
 // Reference citations are relative to /root/reference/metabodecon/src/.
 #include "../../include/mdb200.h"
 #include "kernels.cuh"
-#include "smooth_fast.cuh"
+#include "smooth_lanes.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -617,8 +617,8 @@ static int sm_count()
     return n;
 }
 
-// K1 dispatch: the pipelined TMA-staged kernel when the settings are covered (odd window 3/5/7,
-// 1..10 iterations) and every input row is 16-byte aligned, else one generic pass per launch.
+// K1 dispatch: the lane-per-pass TMA-staged kernel when the settings are covered (window 2..9,
+// up to 32 iterations) and every input row is 16-byte aligned, else one generic pass per launch.
 static mdb_status launch_smooth(cudaStream_t stream, const SpecDesc *d_desc, const std::vector<SpecDesc> &descs,
                                 int iters, int window, std::vector<ProfSpan> *spans)
 {
@@ -629,13 +629,15 @@ static mdb_status launch_smooth(cudaStream_t stream, const SpecDesc *d_desc, con
         pts += (double)d.n;
         aligned = aligned && (((uintptr_t)d.y & 15) == 0) && (((uintptr_t)d.ys & 15) == 0);
     }
-    size_t smem = 0;
-    SmoothFastFn fn = smooth_fast_lookup(window, iters, &smem);
+    int tile = 0;
+    SmoothLanesFn fn = smooth_lanes_lookup(window, iters, &tile);
     const char *force = std::getenv("MDB_SMOOTH_GENERIC");
     prof_begin(spans, MDB_KERNEL_SMOOTH, stream);
     if (fn && aligned && !(force && force[0] == '1')) {
+        const int groups = 32 / iters;  // spectra per warp: one lane per (spectrum, pass)
+        const size_t smem = smooth_lanes_smem_bytes(tile, groups);
         CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        fn<<<(unsigned)((S + 31) / 32), SM_THREADS, smem, stream>>>(d_desc, (int)S);
+        fn<<<(unsigned)((S + groups - 1) / groups), SL_THREADS, smem, stream>>>(d_desc, (int)S, iters);
         LAUNCH_CHECK();
     } else {
         for (int p = 0; p < iters; ++p) {

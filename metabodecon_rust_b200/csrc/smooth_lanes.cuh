@@ -1,0 +1,277 @@
+// smooth_lanes.cuh -- K1, the exact-recurrence moving average with one LANE per (spectrum, pass).
+//
+// smoothing/moving_average.rs:53-83 keeps one running sum per pass,
+//     sum = fl(fl(sum + v[i+r]) - popped);  v[i] = fl(sum * div),
+// and peak parity depends on that exact rounding sequence, so every pass is a
+// strictly sequential chain per spectrum.  What CAN run in parallel:
+//   * the I passes of one spectrum: pass p consumes the output stream of pass p-1, delayed by
+//     (W + r) steps.  Lane p of a group of I lanes owns pass p; its input is what lane p-1 emitted
+//     W steps earlier (one __shfl_up of a W-deep output history, so the shuffle never waits for
+//     the step before it).  Every lane executes the same 3 FP64 instructions per step and the only
+//     loop-carried dependence is each lane's own running sum (2 dependent adds): the kernel runs
+//     at chain latency instead of issuing all I passes from one lane;
+//   * spectra: floor(32 / I) spectra per warp, one warp per CTA, several CTAs per SM;
+//   * memory: the [G spectra x T points] input tile of a warp is staged through shared memory with
+//     one TMA bulk copy per row (cp.async.bulk + mbarrier, 4 stages in flight) and the smoothed
+//     tile goes back with one bulk store per row, so HBM traffic is exactly 8N read + 8N written
+//     per spectrum with full lines although each group walks its own row.
+//
+// State machine of one pass (circular_buffer.rs:34-59 semantics), input index s = 0, 1, ...:
+//   s < r              preload: push, sum += v                                  (:58-61)
+//   r <= s < n         push; if the FIFO was full pop the oldest and subtract it, else
+//                      div = 1/len; emit out[s-r] = sum * div                   (:62-70)
+//   n <= s < n + r     tail: pop, sum -= popped, div = 1/len, emit out[s-r]     (:71-79)
+// The ring slot written at global step tau is (tau mod W) for every lane, so once a FIFO is full
+// its oldest element sits exactly in the slot about to be overwritten and, with the step loop
+// unrolled by W, ring slots are addressed statically (registers).
+#pragma once
+#include "kernels.cuh"
+
+namespace mdb {
+
+// ---- PTX wrappers for the store direction (loads: tma_bulk_g2s / mbarrier_* in kernels.cuh)
+__device__ __forceinline__ bool mbarrier_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void tma_bulk_s2g(void *dst, const void *src_smem, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_addr(src_smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void tma_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+constexpr int SL_STAGES = 4;    // input tiles in flight per warp
+constexpr int SL_OSTAGES = 3;   // output tiles in the ring
+constexpr int SL_THREADS = 32;  // one warp per CTA
+
+// tile length: a multiple of W (static ring slots) and even (16-byte bulk copies), at most 112
+template <int W> struct SmoothTile {
+    static constexpr int Q = 112 / W;
+    static constexpr int T = W * ((W % 2) ? (Q & ~1) : Q);
+};
+
+inline size_t smooth_lanes_smem_bytes(int tile, int groups)
+{
+    return (size_t)(SL_STAGES + SL_OSTAGES) * groups * (tile + 2) * 8 + SL_STAGES * 8 + 64;
+}
+
+template <int W>
+__global__ void __launch_bounds__(SL_THREADS)
+smooth_lanes_kernel(const SpecDesc *__restrict__ sd, int n_spec, int iters)
+{
+    constexpr int T = SmoothTile<W>::T;
+    constexpr int STRIDE = T + 2;  // doubles; (T+2)*8 bytes keeps rows 16-byte aligned
+    constexpr int R = W / 2;
+    static_assert(T % W == 0 && T % 2 == 0, "tile must hold whole ring rotations and 16-byte rows");
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int lane = threadIdx.x;
+    const int G = 32 / iters;                 // spectra per warp
+    const int grp = lane / iters, p = lane - grp * iters;
+    const int s = blockIdx.x * G + grp;
+    const bool valid = grp < G && s < n_spec;
+    const bool first = valid && p == 0, last = valid && p == iters - 1;
+    const int delay = p * (W + R);            // input index of this lane at global step tau: tau - delay
+    const int L = R + (iters - 1) * (W + R);  // output index written at global step tau: tau - L
+
+    double *in_buf = reinterpret_cast<double *>(smem_raw);                 // [SL_STAGES][G][STRIDE]
+    double *out_buf = in_buf + SL_STAGES * G * STRIDE;                     // [SL_OSTAGES][G][STRIDE]
+    uint64_t *full = reinterpret_cast<uint64_t *>(out_buf + SL_OSTAGES * G * STRIDE);
+
+    const double *__restrict__ y = valid ? sd[s].y : nullptr;
+    double *__restrict__ ys = valid ? sd[s].ys : nullptr;
+    const int n = valid ? sd[s].n : 0;
+    const int n_max = __reduce_max_sync(0xffffffffu, n);
+    const int n_min = __reduce_min_sync(0xffffffffu, valid ? n : 0x7fffffff);
+    const int steps = n_max + L + 1;          // every lane has drained by then
+    const int tiles = (steps + T - 1) / T;
+    const int in_tiles = (n_max + T - 1) / T;
+
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < SL_STAGES; ++q) mbarrier_init(&full[q], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+
+    auto issue_load = [&](int k) {  // rows of input tile k, one bulk copy per spectrum of the warp
+        const int stage = k % SL_STAGES;
+        int cnt = first ? n - k * T : 0;
+        cnt = cnt < 0 ? 0 : (cnt > T ? T : cnt);
+        const uint32_t bytes = (uint32_t)(cnt & ~1) * 8u;  // bulk copies move multiples of 16 bytes
+        const uint32_t total = __reduce_add_sync(0xffffffffu, bytes);
+        if (lane == 0) mbarrier_expect_tx(&full[stage], total);
+        __syncwarp();
+        if (bytes) tma_bulk_g2s(in_buf + (stage * G + grp) * STRIDE, y + (size_t)k * T, bytes, &full[stage]);
+    };
+    auto orow = [&](int tile) -> double * { return out_buf + ((tile % SL_OSTAGES) * G + grp) * STRIDE; };
+    auto flush_tile = [&](int j) {  // output tile j of every spectrum: generic-proxy writes -> bulk store
+        fence_proxy_async_smem();
+        __syncwarp();
+        int cnt = last ? n - j * T : 0;
+        cnt = cnt < 0 ? 0 : (cnt > T ? T : cnt);
+        const uint32_t bytes = (uint32_t)(cnt & ~1) * 8u;
+        if (bytes) tma_bulk_s2g(ys + (size_t)j * T, orow(j), bytes);
+        if (cnt & 1) ys[(size_t)j * T + cnt - 1] = orow(j)[cnt - 1];
+        tma_bulk_commit();
+    };
+
+    for (int k = 0; k < SL_STAGES && k < in_tiles; ++k) issue_load(k);
+
+    // ---- per-lane pass state
+    double f[W];
+#pragma unroll
+    for (int k = 0; k < W; ++k) f[k] = 0.0;
+    double o[W];  // outputs of the last W steps: slot (tau mod W) is read by the next lane W steps later
+#pragma unroll
+    for (int k = 0; k < W; ++k) o[k] = 0.0;
+    double sum = 0.0, div = 1.0, out = 0.0;
+    int len = 0, head = 0;
+    auto ring_get = [&](int slot) {
+        double v = f[0];
+#pragma unroll
+        for (int k = 1; k < W; ++k) v = (slot == k) ? f[k] : v;
+        return v;
+    };
+    auto hist_get = [&](int slot) {
+        double v = o[0];
+#pragma unroll
+        for (int k = 1; k < W; ++k) v = (slot == k) ? o[k] : v;
+        return v;
+    };
+    auto hist_set = [&](int slot, double v) {
+#pragma unroll
+        for (int k = 0; k < W; ++k) o[k] = (slot == k) ? v : o[k];
+    };
+    auto ring_set = [&](int slot, double v) {
+#pragma unroll
+        for (int k = 0; k < W; ++k) f[k] = (slot == k) ? v : f[k];
+    };
+
+    // one step of the state machine for any phase; `slot` = tau mod W.  Returns true when an
+    // output (index sidx - R) was produced into `out`.
+    auto general_step = [&](int sidx, int slot, double vin) -> bool {
+        if (!valid || sidx < 0 || sidx >= n + R) return false;
+        if (sidx < n) {
+            sum = __dadd_rn(sum, vin);
+            if (len == W) {  // circular_buffer.rs:35-40: pop the oldest, push into its slot
+                const double popped = ring_get(head);
+                ring_set(slot, vin);
+                head = (head + 1 == W) ? 0 : head + 1;
+                sum = __dsub_rn(sum, popped);
+            } else {
+                if (len == 0) head = slot;
+                ring_set(slot, vin);
+                ++len;
+                if (sidx >= R) div = __ddiv_rn(1.0, (double)len);  // main loop only (:66-68), not the preload
+            }
+            if (sidx < R) return false;
+            out = __dmul_rn(sum, div);
+            return true;
+        }
+        if (len <= 0) return false;  // tail (:71-79)
+        const double popped = ring_get(head);
+        head = (head + 1 == W) ? 0 : head + 1;
+        --len;
+        sum = __dsub_rn(sum, popped);
+        div = __ddiv_rn(1.0, (double)len);
+        out = __dmul_rn(sum, div);
+        return true;
+    };
+
+    for (int k = 0; k < tiles; ++k) {
+        const int stage = k % SL_STAGES;
+        const bool has_input = k < in_tiles;
+        if (has_input) {
+            while (!mbarrier_try_wait(&full[stage], (uint32_t)((k / SL_STAGES) & 1))) {}
+        }
+        double *irow = in_buf + (stage * G + grp) * STRIDE;
+        if (has_input && first) {  // odd trailing element of a row: not part of the 16-byte-granular bulk copy
+            int cnt = n - k * T;
+            cnt = cnt < 0 ? 0 : (cnt > T ? T : cnt);
+            if (cnt & 1) irow[cnt - 1] = y[(size_t)k * T + cnt - 1];
+        }
+        // the ring slot that output tile k will use was flushed SL_OSTAGES tiles ago: make sure it was read
+        tma_bulk_wait_read<1>();
+        __syncwarp();
+
+        const int tau0 = k * T;
+        // outputs of this tile's steps have indices tau - L: the first L of them land in output tile k-1
+        double *__restrict__ pa = orow(k >= 1 ? k - 1 : 0) + (T - L);  // only dereferenced when k >= 1 (fast tiles)
+        double *__restrict__ pb = orow(k) - L;
+        const bool fast = (k >= 1) && (tau0 >= W + (iters - 1) * (W + R)) && (tau0 + T <= n_min);
+        if (fast) {
+            // steady state for every valid lane: FIFO full, static ring slots, no phase logic.
+            // The W inputs of the next rotation are fetched from shared memory one rotation ahead,
+            // so the only latency left on the critical path is the running sum's two adds.
+            double cur[W], nxt[W];
+#pragma unroll
+            for (int u = 0; u < W; ++u) { cur[u] = irow[u]; nxt[u] = 0.0; }
+#pragma unroll 2
+            for (int g = 0; g < T / W; ++g) {
+                if (g + 1 < T / W) {
+#pragma unroll
+                    for (int u = 0; u < W; ++u) nxt[u] = irow[(g + 1) * W + u];
+                }
+#pragma unroll
+                for (int u = 0; u < W; ++u) {
+                    const int j = g * W + u;
+                    const double up = __shfl_up_sync(0xffffffffu, o[u], 1);  // what lane p-1 emitted W steps ago
+                    const double vin = first ? cur[u] : up;
+                    sum = __dsub_rn(__dadd_rn(sum, vin), f[u]);
+                    f[u] = vin;
+                    o[u] = __dmul_rn(sum, div);
+                    if (last) { double *q = (j < L) ? pa : pb; q[j] = o[u]; }
+                }
+#pragma unroll
+                for (int u = 0; u < W; ++u) cur[u] = nxt[u];
+            }
+        } else {
+            for (int j = 0; j < T; ++j) {
+                const int tau = tau0 + j;
+                const int slot = tau % W;
+                double vin = __shfl_up_sync(0xffffffffu, hist_get(slot), 1);
+                if (first && tau < n) vin = irow[j];
+                const int sidx = tau - delay;
+                const bool emitted = general_step(sidx, slot, vin);
+                if (emitted) hist_set(slot, out);
+                if (last && emitted) {
+                    const int o = sidx - R;  // == tau - L
+                    orow(o / T)[o % T] = out;
+                }
+            }
+            // a fast tile may follow: its static addressing needs head == tau mod W, which holds for
+            // every full FIFO (see the header); nothing to normalise
+        }
+        __syncwarp();
+        if (k + SL_STAGES < in_tiles) issue_load(k + SL_STAGES);
+        if (k >= 1) flush_tile(k - 1);
+    }
+    if (tiles >= 1) flush_tile(tiles - 1);
+    tma_bulk_wait_read<0>();
+}
+
+using SmoothLanesFn = void (*)(const SpecDesc *, int, int);
+
+// Returns the kernel for `window` (2..9) and the tile length, or nullptr when the settings need
+// the generic path (window > 9 or more than 32 iterations).
+inline SmoothLanesFn smooth_lanes_lookup(int window, int iterations, int *tile)
+{
+    if (iterations < 1 || iterations > 32) return nullptr;
+    // the output stream lags the input by L = r + (I-1)(W+r) steps; the two-tile output window needs L <= T
+#define MDB_SL_CASE(Wv) \
+    if (window == Wv) { \
+        if ((Wv / 2) + (iterations - 1) * (Wv + Wv / 2) > SmoothTile<Wv>::T) return nullptr; \
+        *tile = SmoothTile<Wv>::T; return smooth_lanes_kernel<Wv>; }
+    MDB_SL_CASE(2) MDB_SL_CASE(3) MDB_SL_CASE(4) MDB_SL_CASE(5) MDB_SL_CASE(6) MDB_SL_CASE(7) MDB_SL_CASE(8) MDB_SL_CASE(9)
+#undef MDB_SL_CASE
+    return nullptr;
+}
+
+}  // namespace mdb
