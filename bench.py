@@ -117,7 +117,7 @@ def run_reference(args, rank, world):
         return
     import oracle as O
     k_true, hw_range, desc = WORKLOADS[args.workload]
-    cores = O.max_threads()
+    cores = O.use_all_cores()
     n_sample = args.cpu_sample or 4 * cores
     x = axis(N_POINTS)
     ys = np.empty((n_sample, N_POINTS))
@@ -223,6 +223,7 @@ def main():
 
     dev_views = make_views(x_dev.data_ptr(), y_dev.data_ptr())
     stats = {}
+    chunk_max = min(512, (1536 << 20) // (48 * N_POINTS + 4096))  # chunk_size_for() in csrc/api.cu
 
     def step(views, memory):
         batch = C.c_void_p()
@@ -285,7 +286,6 @@ def main():
         torch.cuda.synchronize()
         host_views = make_views(x_host.data_ptr(), y_host.data_ptr())
         ms_host, _ = timed(host_views, _lib.MDB_MEM_HOST, max(1, args.warmup), args.steps)
-        chunk_max = min(512, (1536 << 20) // (48 * N_POINTS + 4096))  # chunk_size_for() in csrc/api.cu
         h2d = S * N_POINTS * 8 + N_POINTS * 8 * ((S + chunk_max - 1) // chunk_max)  # intensities + the axis once per chunk
         d2h = stats["lorentzians"] * 24 + stats["peaks"] * 12 + S * (8 + 4 + 48)
         e2e = {"value": world * S / (ms_host / 1e3), "unit": "spectra/s", "h2d_bytes_per_step": int(h2d),
@@ -342,6 +342,18 @@ def main():
     sm_max = clocks["sm_max_mhz"] if clocks else 1965.0
     fp64_peak_tflops = N_SM * FP64_LANES_PER_SM * 2 * sm_max * 1e6 / 1e12  # FMA = 2 flops, at max clock
 
+    traffic_db = {}
+    traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(traffic_path):
+        with open(traffic_path) as fh:
+            traffic_db = json.load(fh).get("bytes_per_spectrum", {})
+    n_chunks = (S + chunk_max - 1) // chunk_max
+    spectra_per_launch = S / n_chunks
+
+    def traffic(name):
+        """DRAM bytes per launch: ncu-measured bytes per spectrum (profiles/traffic.json) x spectra per launch."""
+        return traffic_db[name] * spectra_per_launch if name in traffic_db else None
+
     def fp64_roofline(name):
         p = prof[name]
         if p["launches"] == 0 or p["ms"] <= 0:
@@ -350,7 +362,7 @@ def main():
         achieved = evals_per_s * FLOPS_PER_EVAL / 1e12
         pipe_rate = N_SM * FP64_LANES_PER_SM * sm_mhz * 1e6
         return {"bound": "fp64", "kernel": name, "achieved": achieved, "peak": fp64_peak_tflops, "unit": "TFLOP/s",
-                "frac": achieved / fp64_peak_tflops, "traffic": None,
+                "frac": achieved / fp64_peak_tflops, "traffic": traffic(name),
                 "peak_source": f"computed: {N_SM} SMs x {FP64_LANES_PER_SM} FP64 lanes x 2 x {sm_max:.0f} MHz (not in MEASURED_PEAKS.json)",
                 "evals_per_s": evals_per_s, "evals_per_launch": p["work"] / p["launches"],
                 "ms_per_launch": p["ms"] / p["launches"], "launches": p["launches"],
@@ -363,7 +375,7 @@ def main():
             return None
         achieved = p["work"] / (p["ms"] / 1e3) / 1e9
         return {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": None, "peak_source": hbm_src,
+                "frac": achieved / hbm_peak, "traffic": traffic(name), "peak_source": hbm_src,
                 "bytes_per_launch": p["work"] / p["launches"], "ms_per_launch": p["ms"] / p["launches"],
                 "launches": p["launches"]}
 
@@ -379,7 +391,7 @@ def main():
     parity = None
     if not args.no_cpu_baseline and world == 1:
         import oracle as O
-        cores = O.max_threads()
+        cores = O.use_all_cores()
         n_sample = min(S, args.cpu_sample or 16 * cores)
         ys = y_dev[:n_sample].cpu().numpy()
         O.par_deconvolute_spectra(O.Settings(), x_np, ys[:min(n_sample, cores)], SB)  # warm-up

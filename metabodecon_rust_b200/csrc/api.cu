@@ -432,14 +432,14 @@ struct Workspace {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     // stage A
-    DevBuf x, y, ys, tmp, occ, cl, cc, cr, cs, sfr, sel, ig, desc, sel_out;
+    DevBuf x, y, ys, tmp, tile_cnt, pk, sc, sfr, sel, ig, desc, sel_out;
     PinBuf h_desc, h_ig, h_sel_out;
     // stage B
     DevBuf fdesc, segs, fit_state, par_a, par_b, lor, n_kept, resid, mse, peaks_dense;
     PinBuf h_fdesc, h_segs, h_lor, h_n_kept, h_mse, h_peaks;
     void release()
     {
-        for (DevBuf *b : {&x, &y, &ys, &tmp, &occ, &cl, &cc, &cr, &cs, &sfr, &sel, &ig, &desc, &sel_out, &fdesc,
+        for (DevBuf *b : {&x, &y, &ys, &tmp, &tile_cnt, &pk, &sc, &sfr, &sel, &ig, &desc, &sel_out, &fdesc,
                           &segs, &fit_state, &par_a, &par_b, &lor, &n_kept, &resid, &mse, &peaks_dense})
             b->release();
         for (PinBuf *b : {&h_desc, &h_ig, &h_sel_out, &h_fdesc, &h_segs, &h_lor, &h_n_kept, &h_mse, &h_peaks})
@@ -588,7 +588,7 @@ struct Chunk {
     std::vector<Segment> segs;
     long long p_total = 0;             // selected peaks in the chunk
     long long res_total = 0;
-    int max_words = 0, max_slots = 0, max_peaks = 0, max_seg_len = 0;
+    int max_tiles = 0, max_peaks = 0, max_seg_len = 0;
     bool stage_b_launched = false;
     std::vector<ProfSpan> spans;       // per-kernel timing, resolved in finish_chunk
 };
@@ -656,24 +656,23 @@ static mdb_status stage_a(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
     Workspace &ws = *ck.ws;
     const size_t S = ck.count;
     // ---- layout
-    size_t y_elems = 0, slot_elems = 0, word_elems = 0, ig_elems = 0;
-    std::vector<size_t> y_off(S), slot_off(S), word_off(S), ig_off(S);
+    size_t y_elems = 0, cand_elems = 0, tile_elems = 0, ig_elems = 0;
+    std::vector<size_t> y_off(S), cand_off(S), tile_off(S), ig_off(S);
     std::map<const double *, size_t> x_map;  // caller x pointer -> element offset in ws.x
     size_t x_elems = 0;
-    ck.max_words = ck.max_slots = 0;
+    ck.max_tiles = 0;
     for (size_t s = 0; s < S; ++s) {
         const HostSpec &h = hs[ck.first + s];
         y_off[s] = y_elems;
         y_elems += align_up(h.n, 16);
-        const size_t slots = (h.n + 1) / 2, words = (slots + 31) / 32;
-        slot_off[s] = slot_elems;
-        slot_elems += align_up(slots, 16);
-        word_off[s] = word_elems;
-        word_elems += align_up(words, 4);
+        const size_t tiles = (h.n + DETECT_TILE - 1) / DETECT_TILE;
+        cand_off[s] = cand_elems;
+        cand_elems += tiles * DETECT_CAP;  // candidate capacity: DETECT_CAP records per detection tile
+        tile_off[s] = tile_elems;
+        tile_elems += align_up(tiles, 4);
         ig_off[s] = ig_elems;
         ig_elems += h.ig.size();
-        ck.max_words = std::max(ck.max_words, (int)words);
-        ck.max_slots = std::max(ck.max_slots, (int)slots);
+        ck.max_tiles = std::max(ck.max_tiles, (int)tiles);
         if (memory == MDB_MEM_HOST && !x_map.count(h.x)) {
             x_map[h.x] = x_elems;
             x_elems += align_up(h.n, 16);
@@ -687,13 +686,11 @@ static mdb_status stage_a(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
     }
     CUDA_TRY(ws.ys.ensure(y_elems * 8));
     if (need_tmp) CUDA_TRY(ws.tmp.ensure(y_elems * 8));
-    CUDA_TRY(ws.occ.ensure(word_elems * 4));
-    CUDA_TRY(ws.cl.ensure(slot_elems * 4));
-    CUDA_TRY(ws.cc.ensure(slot_elems * 4));
-    CUDA_TRY(ws.cr.ensure(slot_elems * 4));
-    CUDA_TRY(ws.cs.ensure(slot_elems * 8));
-    CUDA_TRY(ws.sfr.ensure(slot_elems * 8));
-    CUDA_TRY(ws.sel.ensure(slot_elems * 12));
+    CUDA_TRY(ws.tile_cnt.ensure(tile_elems * 4));
+    CUDA_TRY(ws.pk.ensure(cand_elems * 12));
+    CUDA_TRY(ws.sc.ensure(cand_elems * 8));
+    CUDA_TRY(ws.sfr.ensure(cand_elems * 8));
+    CUDA_TRY(ws.sel.ensure(cand_elems * 12));
     CUDA_TRY(ws.ig.ensure(std::max<size_t>(ig_elems, 1) * 4));
     CUDA_TRY(ws.desc.ensure(S * sizeof(SpecDesc)));
     CUDA_TRY(ws.sel_out.ensure(S * sizeof(SelectOut)));
@@ -716,22 +713,18 @@ static mdb_status stage_a(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
         }
         d.ys = ws.ys.as<double>() + y_off[s];
         d.tmp = need_tmp ? ws.tmp.as<double>() + y_off[s] : nullptr;
-        d.occ = ws.occ.as<uint32_t>() + word_off[s];
-        d.cl = ws.cl.as<int>() + slot_off[s];
-        d.cc = ws.cc.as<int>() + slot_off[s];
-        d.cr = ws.cr.as<int>() + slot_off[s];
-        d.cs = ws.cs.as<double>() + slot_off[s];
-        d.sfr = ws.sfr.as<double>() + slot_off[s];
-        d.sel = ws.sel.as<int>() + 3 * slot_off[s];
+        d.tile_cnt = ws.tile_cnt.as<int>() + tile_off[s];
+        d.pk = ws.pk.as<int>() + 3 * cand_off[s];
+        d.sc = ws.sc.as<double>() + cand_off[s];
+        d.sfr = ws.sfr.as<double>() + cand_off[s];
+        d.sel = ws.sel.as<int>() + 3 * cand_off[s];
         d.ig = ws.ig.as<int>() + ig_off[s];
         d.n = (int)h.n;
-        d.n_slots = (int)((h.n + 1) / 2);
-        d.n_words = (d.n_slots + 31) / 32;
+        d.n_tiles = (int)((h.n + DETECT_TILE - 1) / DETECT_TILE);
         d.sb0 = h.sb_i0;
         d.sb1 = h.sb_i1;
         d.n_ig = (int)(h.ig.size() / 2);
         d.has_ig = dc.has_ignore ? 1 : 0;
-        d.pad_ = 0;
         for (size_t q = 0; q < h.ig.size(); ++q) h_ig[ig_off[s] + q] = h.ig[q];
     }
     std::memcpy(ws.h_desc.p, ck.desc.data(), S * sizeof(SpecDesc));
@@ -782,7 +775,7 @@ static mdb_status stage_a(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
     }
     // ---- K2/K3 detection + scoring
     {
-        dim3 grid((unsigned)((ck.max_slots + DETECT_THREADS - 1) / DETECT_THREADS), (unsigned)S);
+        dim3 grid((unsigned)ck.max_tiles, (unsigned)S);
         double pts = 0.0;
         for (size_t s = 0; s < S; ++s) pts += (double)ck.desc[s].n;
         prof_begin(&ck.spans, MDB_KERNEL_DETECT, ws.stream);
@@ -792,7 +785,7 @@ static mdb_status stage_a(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
     }
     // ---- K4 selection
     {
-        const size_t smem = (size_t)3 * ck.max_words * sizeof(int);
+        const size_t smem = (size_t)4 * ck.max_tiles * sizeof(int);
         if ((int)smem + 1024 > smem_optin_limit())
             return fail(MDB_ERR_UNSUPPORTED, "spectrum too long for the selection kernel's shared-memory masks");
         if (smem > 40 * 1024)
@@ -1239,28 +1232,26 @@ extern "C" mdb_status mdb_stage_detect(const double *smoothed, size_t n, int32_t
     ck.ws = ws;
     std::vector<HostSpec> hs;
     if ((st = stage_a_single(*dc, smoothed, n, 0, n, 0, nullptr, 0, ck, hs)) != MDB_OK) return st;
-    // download the slot arrays and walk the occupancy mask in order (test-only path)
+    // download the per-tile candidate lists and concatenate them in tile order (test-only path)
     const SpecDesc &d = ck.desc[0];
-    std::vector<uint32_t> occ(d.n_words);
-    std::vector<int> cl(d.n_slots), cc(d.n_slots), cr(d.n_slots);
-    std::vector<double> cs(d.n_slots);
+    std::vector<int> tile_cnt(d.n_tiles);
     CUDA_TRY(cudaStreamSynchronize(ws->stream));
-    CUDA_TRY(cudaMemcpy(occ.data(), d.occ, (size_t)d.n_words * 4, cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(cl.data(), d.cl, (size_t)d.n_slots * 4, cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(cc.data(), d.cc, (size_t)d.n_slots * 4, cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(cr.data(), d.cr, (size_t)d.n_slots * 4, cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaMemcpy(cs.data(), d.cs, (size_t)d.n_slots * 8, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(tile_cnt.data(), d.tile_cnt, (size_t)d.n_tiles * 4, cudaMemcpyDeviceToHost));
+    std::vector<int> pk(3 * (size_t)DETECT_CAP);
+    std::vector<double> sc(DETECT_CAP);
     size_t k = 0;
-    for (int w = 0; w < d.n_words; ++w)
-        for (int j = 0; j < 32; ++j)
-            if (occ[w] & (1u << j)) {
-                const int slot = w * 32 + j;
-                if (k < cap) {
-                    peaks[3 * k] = cl[slot]; peaks[3 * k + 1] = cc[slot]; peaks[3 * k + 2] = cr[slot];
-                    scores[k] = cs[slot];
-                }
-                ++k;
+    for (int t = 0; t < d.n_tiles; ++t) {
+        const int c = tile_cnt[t];
+        if (c == 0) continue;
+        CUDA_TRY(cudaMemcpy(pk.data(), d.pk + 3 * (size_t)t * DETECT_CAP, (size_t)c * 12, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(sc.data(), d.sc + (size_t)t * DETECT_CAP, (size_t)c * 8, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < c; ++i, ++k) {
+            if (k < cap) {
+                peaks[3 * k] = pk[3 * i]; peaks[3 * k + 1] = pk[3 * i + 1]; peaks[3 * k + 2] = pk[3 * i + 2];
+                scores[k] = sc[i];
             }
+        }
+    }
     *n_found = k;
     return MDB_OK;
 }

@@ -344,3 +344,15 @@ def par_deconvolute_spectra(settings: Settings, x, ys, sb):
 
 def max_threads() -> int:
     return lib().orc_max_threads()
+
+
+def use_all_cores() -> int:
+    """Size the OpenMP pool to every core this process may run on (torchrun exports
+    OMP_NUM_THREADS=1, which would otherwise make the CPU baseline single-threaded)."""
+    import os
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    lib().orc_set_num_threads(C.c_int(n))
+    return max_threads()

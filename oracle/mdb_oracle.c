@@ -644,6 +644,17 @@ int orc_par_deconvolute_spectra(const orc_settings *st, size_t n_spectra, const 
     return ORC_OK;
 }
 
+/* bench.py's reference arm runs under torchrun, which exports OMP_NUM_THREADS=1: let the caller
+ * ask for all host cores explicitly. */
+void orc_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int orc_max_threads(void)
 {
 #ifdef _OPENMP
