@@ -775,7 +775,7 @@ static mdb_status stage_a(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
     }
     // ---- K2/K3 detection + scoring
     {
-        dim3 grid((unsigned)ck.max_tiles, (unsigned)S);
+        dim3 grid((unsigned)((ck.max_tiles + DETECT_WARPS - 1) / DETECT_WARPS), (unsigned)S);
         double pts = 0.0;
         for (size_t s = 0; s < S; ++s) pts += (double)ck.desc[s].n;
         prof_begin(&ck.spans, MDB_KERNEL_DETECT, ws.stream);
