@@ -211,6 +211,16 @@ mdb_status mdb_deconvolute_spectra(const mdb_deconvoluter *d, const mdb_spectrum
                                    size_t n_spectra, int memory, mdb_batch **out);
 
 /*
+ * Deconvoluter::optimize_settings  (deconvoluter.rs:761-825): deconvolutes `reference` under 27
+ * smoothing x 10 selection x 3 fitting settings (810 combinations, same grids and iteration order
+ * as the reference), stores the combination with the lowest MSE in the deconvoluter (first minimum
+ * wins) and writes that MSE to *mse.  Any failing combination aborts with its status and leaves
+ * the deconvoluter unchanged.  Ignore regions of the deconvoluter apply.
+ */
+mdb_status mdb_deconvoluter_optimize_settings(mdb_deconvoluter *d, const mdb_spectrum_view *reference,
+                                              int memory, double *mse);
+
+/*
  * Lorentzian::superposition_vec / par_superposition_vec  (lorentzian.rs:631-635, 656-663):
  * out[i] = sum_j sfhw_j / (hw2_j + (x_i - maxp_j)^2), j ascending, one rounding per operation.
  * memory applies to x, lorentzians and out alike.

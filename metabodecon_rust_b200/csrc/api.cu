@@ -533,6 +533,10 @@ struct HostSpec {
     std::vector<int> ig;                       // flattened (start, end) index pairs
     std::vector<std::pair<int, int>> ranges;   // MSE ranges (deconvoluter.rs:828-845)
     int pre_status = MDB_OK;                   // status known before any launch
+    // per-spectrum overrides (optimize_settings runs one spectrum under many settings)
+    const double *ys_dev = nullptr;            // already-smoothed intensities in device memory
+    double threshold = 0.0;                    // selection threshold
+    int fit_iters = 0;                         // refinement passes
 };
 
 struct SpecResult {
@@ -678,13 +682,14 @@ static mdb_status stage_a(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
             x_elems += align_up(h.n, 16);
         }
     }
-    const bool ma = dc.smoothing.kind == MDB_SMOOTHING_MOVING_AVERAGE && !skip_smoothing_input_is_smoothed;
+    const bool preset = hs[ck.first].ys_dev != nullptr;  // smoothed rows supplied by the caller (all or none)
+    const bool ma = dc.smoothing.kind == MDB_SMOOTHING_MOVING_AVERAGE && !skip_smoothing_input_is_smoothed && !preset;
     const bool need_tmp = ma && dc.smoothing.iterations >= 2;
     if (memory == MDB_MEM_HOST) {
         CUDA_TRY(ws.x.ensure(x_elems * 8));
         CUDA_TRY(ws.y.ensure(y_elems * 8));
     }
-    CUDA_TRY(ws.ys.ensure(y_elems * 8));
+    if (!preset) CUDA_TRY(ws.ys.ensure(y_elems * 8));
     if (need_tmp) CUDA_TRY(ws.tmp.ensure(y_elems * 8));
     CUDA_TRY(ws.tile_cnt.ensure(tile_elems * 4));
     CUDA_TRY(ws.pk.ensure(cand_elems * 12));
@@ -711,7 +716,8 @@ static mdb_status stage_a(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
             d.x = h.x;
             d.y = h.y;
         }
-        d.ys = ws.ys.as<double>() + y_off[s];
+        d.ys = h.ys_dev ? const_cast<double *>(h.ys_dev) : ws.ys.as<double>() + y_off[s];
+        d.threshold = h.threshold;
         d.tmp = need_tmp ? ws.tmp.as<double>() + y_off[s] : nullptr;
         d.tile_cnt = ws.tile_cnt.as<int>() + tile_off[s];
         d.pk = ws.pk.as<int>() + 3 * cand_off[s];
@@ -762,7 +768,7 @@ static mdb_status stage_a(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
 
     const SpecDesc *d_desc = ws.desc.as<SpecDesc>();
     // ---- K1 smoothing (deconvoluter.rs:531-532)
-    if (!skip_smoothing_input_is_smoothed) {
+    if (!skip_smoothing_input_is_smoothed && !preset) {
         if (ma) {
             mdb_status sst = launch_smooth(ws.stream, d_desc, ck.desc, (int)dc.smoothing.iterations,
                                            (int)dc.smoothing.window_size, &ck.spans);
@@ -792,7 +798,7 @@ static mdb_status stage_a(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
             CUDA_TRY(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         prof_begin(&ck.spans, MDB_KERNEL_SELECT, ws.stream);
         select_kernel<<<(unsigned)S, SELECT_THREADS, smem, ws.stream>>>(d_desc, ws.sel_out.as<SelectOut>(),
-                                                                       dc.selection.kind, dc.selection.threshold);
+                                                                       dc.selection.kind);
         LAUNCH_CHECK();
         prof_end(&ck.spans, ws.stream, (double)S);
     }
@@ -816,6 +822,7 @@ static void fit_state_pointers(Workspace &ws, long long p_total, FitState &st)
 static mdb_status stage_b(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_deconvoluter &dc,
                           std::vector<SpecResult> &results, bool with_mse, mdb_lorentzian *trace)
 {
+    (void)dc;  // per-spectrum settings travel in HostSpec since optimize_settings
     Workspace &ws = *ck.ws;
     const size_t S = ck.count;
     CUDA_TRY(cudaEventSynchronize(ws.ev_a));
@@ -836,6 +843,7 @@ static mdb_status stage_b(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
         f.n_peaks = (r.status == MDB_OK) ? so[s].n_selected : 0;
         f.seg_off = (int)ck.segs.size();
         f.seg_cnt = 0;
+        f.n_iters = h.fit_iters;
         if (r.status == MDB_OK && with_mse) {
             for (auto &rg : h.ranges) {
                 Segment sg;
@@ -878,36 +886,34 @@ static mdb_status stage_b(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
     const FitDesc *d_fd = ws.fdesc.as<FitDesc>();
     FitState st;
     fit_state_pointers(ws, ck.p_total, st);
-    const int iters = (int)dc.fitting.iterations;
-    const double *final_par = st.pa;
+    int iters = 0;  // refinement launches: the largest per-spectrum count of the chunk
+    for (size_t s = 0; s < S; ++s) iters = std::max(iters, ck.fdesc[s].n_peaks > 0 ? ck.fdesc[s].n_iters : 0);
     if (ck.p_total > 0) {
         dim3 grid((unsigned)((ck.max_peaks + FIT_THREADS - 1) / FIT_THREADS), (unsigned)S);
         prof_begin(&ck.spans, MDB_KERNEL_FIT_INIT, ws.stream);
         fit_init_kernel<<<grid, FIT_THREADS, 0, ws.stream>>>(d_desc, d_fd, st, ws.peaks_dense.as<int>());
         LAUNCH_CHECK();
         prof_end(&ck.spans, ws.stream, (double)ck.p_total);
-        double evals_per_pass = 0.0;  // E_fit per pass = 3 * P_s^2
-        for (size_t s = 0; s < S; ++s) evals_per_pass += 3.0 * (double)ck.fdesc[s].n_peaks * (double)ck.fdesc[s].n_peaks;
         // trace is a single-spectrum facility (mdb_stage_fit): p_total carries alignment padding, n_peaks does not
         const size_t n_trace = (size_t)ck.fdesc[0].n_peaks;
         if (trace) {
             CUDA_TRY(cudaMemcpyAsync(trace, st.pa, n_trace * 24, cudaMemcpyDeviceToHost, ws.stream));
         }
-        double *pin = st.pa, *pout = st.pb;
         for (int it = 0; it < iters; ++it) {
+            double evals = 0.0;  // E_fit of this pass = sum of 3 * P_s^2 over the spectra still iterating
+            for (size_t s = 0; s < S; ++s)
+                if (it < ck.fdesc[s].n_iters) evals += 3.0 * (double)ck.fdesc[s].n_peaks * (double)ck.fdesc[s].n_peaks;
             prof_begin(&ck.spans, MDB_KERNEL_FIT_ITER, ws.stream);
-            fit_iter_kernel<<<grid, FIT_THREADS, LOR_SMEM_BYTES, ws.stream>>>(d_fd, st, pin, pout);
+            fit_iter_kernel<<<grid, FIT_THREADS, LOR_SMEM_BYTES, ws.stream>>>(d_fd, st, it);
             LAUNCH_CHECK();
-            prof_end(&ck.spans, ws.stream, evals_per_pass);
+            prof_end(&ck.spans, ws.stream, evals);
             if (trace)
-                CUDA_TRY(cudaMemcpyAsync(trace + (size_t)(it + 1) * n_trace, pout, n_trace * 24,
+                CUDA_TRY(cudaMemcpyAsync(trace + (size_t)(it + 1) * n_trace, (it & 1) ? st.pa : st.pb, n_trace * 24,
                                          cudaMemcpyDeviceToHost, ws.stream));
-            std::swap(pin, pout);
         }
-        final_par = pin;
     }
     prof_begin(&ck.spans, MDB_KERNEL_RETAIN, ws.stream);
-    retain_kernel<<<(unsigned)S, RETAIN_THREADS, 0, ws.stream>>>(d_fd, final_par, ws.lor.as<double>(), ws.n_kept.as<int>());
+    retain_kernel<<<(unsigned)S, RETAIN_THREADS, 0, ws.stream>>>(d_fd, st.pa, st.pb, ws.lor.as<double>(), ws.n_kept.as<int>());
     LAUNCH_CHECK();
     prof_end(&ck.spans, ws.stream, (double)ck.p_total);
     if (with_mse && n_seg) {
@@ -1001,6 +1007,8 @@ static mdb_status build_host_specs(const mdb_deconvoluter &dc, const mdb_spectru
         h.n = v.len;
         h.sb[0] = v.signal_boundaries[0];
         h.sb[1] = v.signal_boundaries[1];
+        h.threshold = dc.selection.threshold;
+        h.fit_iters = (int)std::min<uint64_t>(dc.fitting.iterations, (uint64_t)INT_MAX);
         auto it = x01.find(h.x);
         if (it == x01.end()) {
             double two[2];
@@ -1015,6 +1023,57 @@ static mdb_status build_host_specs(const mdb_deconvoluter &dc, const mdb_spectru
         precompute_spec(h, dc);
     }
     return MDB_OK;
+}
+
+// The chunked pipeline over a prepared list of spectra.  Three workspaces in flight: stage A of
+// chunk k+1 is queued before the host waits for the counts of chunk k, and chunk k-1 is unpacked
+// while chunk k runs its fit / MSE kernels.
+static mdb_status run_pipeline(const mdb_deconvoluter &dc, const std::vector<HostSpec> &hs, int memory,
+                               std::vector<SpecResult> &results)
+{
+    const size_t n_spectra = hs.size();
+    mdb_status st = MDB_OK;
+    // Three workspaces in flight: stage A of chunk k+1 is queued before the host waits for the
+    // counts of chunk k, and chunk k-1 is unpacked while chunk k runs its fit / MSE kernels.
+    const size_t csz_max = chunk_size_for(hs);
+    const size_t n_chunks = (n_spectra + csz_max - 1) / csz_max;
+    const size_t csz = (n_spectra + n_chunks - 1) / n_chunks;  // equal-sized chunks, no straggler
+    size_t depth = 3;
+    if (const char *env = std::getenv("MDB_PIPELINE_DEPTH"))
+        if (std::atoi(env) >= 1) depth = (size_t)std::min(std::atoi(env), 8);
+    const size_t n_ws = std::min<size_t>(depth, n_chunks);
+    std::vector<Workspace *> wss(n_ws, nullptr);
+    auto cleanup = [&]() {
+        for (Workspace *w : wss)
+            if (w) { cudaStreamSynchronize(w->stream); release_workspace(w); }
+    };
+    for (size_t i = 0; i < n_ws; ++i)
+        if ((st = acquire_workspace(&wss[i])) != MDB_OK) { cleanup(); return st; }
+    std::vector<Chunk> chunks(n_chunks);
+    for (size_t k = 0; k < n_chunks; ++k) {
+        chunks[k].ws = wss[k % n_ws];
+        chunks[k].first = k * csz;
+        chunks[k].count = std::min(csz, n_spectra - k * csz);
+    }
+    st = stage_a(chunks[0], hs, dc, memory, false);
+    for (size_t k = 0; st == MDB_OK && k < n_chunks; ++k) {
+        if (n_ws == 1) {  // strictly serial (used for per-kernel profiling): A(k) B(k) finish(k) A(k+1)
+            st = stage_b(chunks[k], hs, dc, results, true, nullptr);
+            if (st == MDB_OK) st = finish_chunk(chunks[k], results, true);
+            if (st == MDB_OK && k + 1 < n_chunks) st = stage_a(chunks[k + 1], hs, dc, memory, false);
+            continue;
+        }
+        if (k + 1 < n_chunks) {
+            if (k + 1 >= n_ws) st = finish_chunk(chunks[k + 1 - n_ws], results, true);  // frees that workspace
+            if (st == MDB_OK) st = stage_a(chunks[k + 1], hs, dc, memory, false);
+        }
+        if (st == MDB_OK) st = stage_b(chunks[k], hs, dc, results, true, nullptr);
+    }
+    if (n_ws > 1)
+        for (size_t k = (n_chunks >= n_ws ? n_chunks - n_ws : 0); st == MDB_OK && k < n_chunks; ++k)
+            if (chunks[k].stage_b_launched) st = finish_chunk(chunks[k], results, true);
+    cleanup();
+    return st;
 }
 
 extern "C" size_t mdb_batch_len(const mdb_batch *b) { return b ? b->r.size() : 0; }
@@ -1060,46 +1119,7 @@ extern "C" mdb_status mdb_deconvolute_spectra(const mdb_deconvoluter *d, const m
     std::vector<HostSpec> hs;
     if ((st = build_host_specs(*d, spectra, n_spectra, memory, hs)) != MDB_OK) return st;
 
-    // Three workspaces in flight: stage A of chunk k+1 is queued before the host waits for the
-    // counts of chunk k, and chunk k-1 is unpacked while chunk k runs its fit / MSE kernels.
-    const size_t csz_max = chunk_size_for(hs);
-    const size_t n_chunks = (n_spectra + csz_max - 1) / csz_max;
-    const size_t csz = (n_spectra + n_chunks - 1) / n_chunks;  // equal-sized chunks, no straggler
-    size_t depth = 3;
-    if (const char *env = std::getenv("MDB_PIPELINE_DEPTH"))
-        if (std::atoi(env) >= 1) depth = (size_t)std::min(std::atoi(env), 8);
-    const size_t n_ws = std::min<size_t>(depth, n_chunks);
-    std::vector<Workspace *> wss(n_ws, nullptr);
-    auto cleanup = [&]() {
-        for (Workspace *w : wss)
-            if (w) { cudaStreamSynchronize(w->stream); release_workspace(w); }
-    };
-    for (size_t i = 0; i < n_ws; ++i)
-        if ((st = acquire_workspace(&wss[i])) != MDB_OK) { cleanup(); return st; }
-    std::vector<Chunk> chunks(n_chunks);
-    for (size_t k = 0; k < n_chunks; ++k) {
-        chunks[k].ws = wss[k % n_ws];
-        chunks[k].first = k * csz;
-        chunks[k].count = std::min(csz, n_spectra - k * csz);
-    }
-    st = stage_a(chunks[0], hs, *d, memory, false);
-    for (size_t k = 0; st == MDB_OK && k < n_chunks; ++k) {
-        if (n_ws == 1) {  // strictly serial (used for per-kernel profiling): A(k) B(k) finish(k) A(k+1)
-            st = stage_b(chunks[k], hs, *d, batch->r, true, nullptr);
-            if (st == MDB_OK) st = finish_chunk(chunks[k], batch->r, true);
-            if (st == MDB_OK && k + 1 < n_chunks) st = stage_a(chunks[k + 1], hs, *d, memory, false);
-            continue;
-        }
-        if (k + 1 < n_chunks) {
-            if (k + 1 >= n_ws) st = finish_chunk(chunks[k + 1 - n_ws], batch->r, true);  // frees that workspace
-            if (st == MDB_OK) st = stage_a(chunks[k + 1], hs, *d, memory, false);
-        }
-        if (st == MDB_OK) st = stage_b(chunks[k], hs, *d, batch->r, true, nullptr);
-    }
-    if (n_ws > 1)
-        for (size_t k = (n_chunks >= n_ws ? n_chunks - n_ws : 0); st == MDB_OK && k < n_chunks; ++k)
-            if (chunks[k].stage_b_launched) st = finish_chunk(chunks[k], batch->r, true);
-    cleanup();
+    st = run_pipeline(*d, hs, memory, batch->r);
     if (st != MDB_OK) return st;
     mdb_status first = MDB_OK;
     for (size_t s = 0; s < n_spectra; ++s)
@@ -1110,6 +1130,98 @@ extern "C" mdb_status mdb_deconvolute_spectra(const mdb_deconvoluter *d, const m
         }
     *out = batch.release();
     return first;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Deconvoluter::optimize_settings  deconvoluter.rs:761-825
+// 27 smoothing settings (iterations 2..=10 x window 3,5,7) x 10 thresholds (5 + c*3/9) x 3 fit
+// iteration counts (5,10,15) = 810 deconvolutions of one spectrum, argmin MSE (first minimum in
+// iteration order, Iterator::min_by).  On the GPU: the output of pass k of a 10-pass smoothing is
+// the k-iteration result, so three all-passes runs (one per window) give all 27 smoothed curves;
+// the 810 (smoothing, threshold, iterations) variants then go through the ordinary chunk pipeline
+// as "spectra" sharing x, y and one of the 27 smoothed rows.
+// ---------------------------------------------------------------------------------------------
+extern "C" mdb_status mdb_deconvoluter_optimize_settings(mdb_deconvoluter *d, const mdb_spectrum_view *spectrum,
+                                                         int memory, double *mse_out)
+{
+    if (!d || !spectrum || !spectrum->chemical_shifts || !spectrum->intensities)
+        return fail(MDB_ERR_INVALID_ARGUMENT, "mdb_deconvoluter_optimize_settings: null argument");
+    if (memory != MDB_MEM_HOST && memory != MDB_MEM_DEVICE) return fail(MDB_ERR_INVALID_ARGUMENT, "unknown memory kind");
+    const size_t n = spectrum->len;
+    if (n < 5 || n >= ((size_t)1 << 31)) return fail(MDB_ERR_INVALID_ARGUMENT, "length must be in [5, 2^31)");
+    mdb_status st = require_device();
+    if (st != MDB_OK) return st;
+
+    const int windows[3] = {3, 5, 7};
+    const int max_iters = 10;
+    const size_t stride = align_up(n, 16);
+    DevBuf xb, yb, ysb, jobb;
+    struct Free { DevBuf *b[4]; ~Free() { for (DevBuf *p : b) p->release(); } } guard{{&xb, &yb, &ysb, &jobb}};
+    CUDA_TRY(ysb.ensure(3 * (size_t)max_iters * stride * 8));
+    CUDA_TRY(jobb.ensure(3 * sizeof(SmoothAllJob)));
+    const double *dx = spectrum->chemical_shifts, *dy = spectrum->intensities;
+    cudaStream_t stream = nullptr;  // the legacy default stream orders these few preparatory operations
+    if (memory == MDB_MEM_HOST) {
+        CUDA_TRY(xb.ensure(stride * 8));
+        CUDA_TRY(yb.ensure(stride * 8));
+        CUDA_TRY(cudaMemcpy(xb.p, spectrum->chemical_shifts, n * 8, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(yb.p, spectrum->intensities, n * 8, cudaMemcpyHostToDevice));
+        dx = xb.as<double>();
+        dy = yb.as<double>();
+    }
+    SmoothAllJob jobs[3];
+    for (int w = 0; w < 3; ++w) {
+        jobs[w].y = dy;
+        jobs[w].out = ysb.as<double>() + (size_t)w * max_iters * stride;
+        jobs[w].stride = (long long)stride;
+        jobs[w].n = (int)n;
+        jobs[w].iters = max_iters;
+        jobs[w].window = windows[w];
+    }
+    CUDA_TRY(cudaMemcpy(jobb.p, jobs, sizeof(jobs), cudaMemcpyHostToDevice));
+    smooth_all_passes_kernel<<<3, 32, 0, stream>>>(jobb.as<SmoothAllJob>());
+    LAUNCH_CHECK();
+    CUDA_TRY(cudaDeviceSynchronize());
+
+    // ---- the 810 variants in the reference's iteration order: smoothing (iterations outer, window
+    // inner), then threshold, then fit iterations
+    struct Variant { int iterations, window; double threshold; int fit; };
+    std::vector<Variant> variants;
+    for (int iterations = 2; iterations <= 10; ++iterations)
+        for (int w = 0; w < 3; ++w)
+            for (int c = 0; c < 10; ++c)
+                for (int fit = 5; fit <= 15; fit += 5)
+                    variants.push_back({iterations, w, 5.0 + (double)c * (8.0 - 5.0) / 9.0, fit});
+    mdb_deconvoluter work = *d;
+    work.selection.kind = MDB_SELECTION_NOISE_SCORE_FILTER;
+    work.selection.scoring_method = MDB_SCORING_MINIMUM_SUM;
+    work.smoothing.kind = MDB_SMOOTHING_MOVING_AVERAGE;
+    mdb_spectrum_view view = *spectrum;
+    view.chemical_shifts = dx;
+    view.intensities = dy;
+    std::vector<mdb_spectrum_view> views(variants.size(), view);
+    std::vector<HostSpec> hs;
+    if ((st = build_host_specs(work, views.data(), views.size(), MDB_MEM_DEVICE, hs)) != MDB_OK) return st;
+    for (size_t v = 0; v < variants.size(); ++v) {
+        hs[v].ys_dev = ysb.as<double>() + ((size_t)variants[v].window * max_iters + (size_t)(variants[v].iterations - 1)) * stride;
+        hs[v].threshold = variants[v].threshold;
+        hs[v].fit_iters = variants[v].fit;
+    }
+    std::vector<SpecResult> results(variants.size());
+    if ((st = run_pipeline(work, hs, MDB_MEM_DEVICE, results)) != MDB_OK) return st;
+    size_t best = 0;
+    for (size_t v = 0; v < variants.size(); ++v) {
+        if (results[v].status != MDB_OK)  // any failing combination aborts the optimisation (:805-812)
+            return fail((mdb_status)results[v].status, std::string("optimize_settings: ") + status_text(results[v].status));
+        if (results[v].mse != results[v].mse)  // partial_cmp(..).unwrap() panics on NaN (:813)
+            return fail(MDB_ERR_REFERENCE_PANIC, "optimize_settings: NaN mean squared error");
+        if (results[v].mse < results[best].mse) best = v;  // strict: the first minimum wins, as Iterator::min_by
+    }
+    d->smoothing = {MDB_SMOOTHING_MOVING_AVERAGE, (uint64_t)variants[best].iterations, (uint64_t)windows[variants[best].window]};
+    d->selection = {MDB_SELECTION_NOISE_SCORE_FILTER, MDB_SCORING_MINIMUM_SUM, variants[best].threshold};
+    d->fitting = {MDB_FITTING_ANALYTICAL, (uint64_t)variants[best].fit};
+    if (mse_out) *mse_out = results[best].mse;
+    return MDB_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1206,6 +1318,8 @@ static mdb_status stage_a_single(const mdb_deconvoluter &dc, const double *smoot
     h.n = n;
     h.sb_i0 = clamp_idx(sb0);
     h.sb_i1 = clamp_idx(sb1);
+    h.threshold = dc.selection.threshold;
+    h.fit_iters = (int)std::min<uint64_t>(dc.fitting.iterations, (uint64_t)INT_MAX);
     if (has_ig)
         for (size_t q = 0; q < 2 * n_ig; ++q) h.ig.push_back(clamp_idx(ig[q]));
     mdb_deconvoluter local = dc;
@@ -1331,6 +1445,7 @@ extern "C" mdb_status mdb_stage_fit(const double *x, const double *y, size_t n, 
     CUDA_TRY(cudaEventRecord(ws->ev_a, ws->stream));
     std::vector<HostSpec> hs(1);
     hs[0].n = n;
+    hs[0].fit_iters = (int)std::min<uint64_t>(iterations, (uint64_t)INT_MAX);
     std::vector<SpecResult> res(1);
     if ((st = stage_b(ck, hs, *dc, res, false, trace)) != MDB_OK) return st;
     if ((st = finish_chunk(ck, res, false)) != MDB_OK) return st;

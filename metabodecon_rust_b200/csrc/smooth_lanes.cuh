@@ -60,6 +60,68 @@ inline size_t smooth_lanes_smem_bytes(int tile, int groups)
     return (size_t)(SL_STAGES + SL_OSTAGES) * groups * (tile + 2) * 8 + SL_STAGES * 8 + 64;
 }
 
+// State of one moving-average pass held by one lane: FIFO ring (slot written at global step tau is
+// tau mod W), running sum, reciprocal length, and a W-deep history of its own outputs.
+template <int W>
+struct PassState {
+    double f[W];   // FIFO contents
+    double o[W];   // outputs of the last W steps: slot (tau mod W) is read by the next lane W steps later
+    double sum, div, out;
+    int len, head;
+
+    __device__ __forceinline__ void reset()
+    {
+#pragma unroll
+        for (int k = 0; k < W; ++k) { f[k] = 0.0; o[k] = 0.0; }
+        sum = 0.0; div = 1.0; out = 0.0; len = 0; head = 0;
+    }
+    __device__ __forceinline__ static double pick(const double (&a)[W], int slot)
+    {
+        double v = a[0];
+#pragma unroll
+        for (int k = 1; k < W; ++k) v = (slot == k) ? a[k] : v;
+        return v;
+    }
+    __device__ __forceinline__ static void put(double (&a)[W], int slot, double v)
+    {
+#pragma unroll
+        for (int k = 0; k < W; ++k) a[k] = (slot == k) ? v : a[k];
+    }
+    // One step of the state machine for any phase; sidx = input index of this pass at this step,
+    // slot = tau mod W, n = spectrum length.  Returns true when an output (index sidx - W/2) was
+    // produced into `out` (and recorded in the history).
+    __device__ __forceinline__ bool step(bool valid, int sidx, int slot, double vin, int n)
+    {
+        constexpr int R = W / 2;
+        if (!valid || sidx < 0 || sidx >= n + R) return false;
+        if (sidx < n) {
+            sum = __dadd_rn(sum, vin);
+            if (len == W) {  // circular_buffer.rs:35-40: pop the oldest, push into its slot
+                const double popped = pick(f, head);
+                put(f, slot, vin);
+                head = (head + 1 == W) ? 0 : head + 1;
+                sum = __dsub_rn(sum, popped);
+            } else {
+                if (len == 0) head = slot;
+                put(f, slot, vin);
+                ++len;
+                if (sidx >= R) div = __ddiv_rn(1.0, (double)len);  // main loop only (:66-68), not the preload
+            }
+            if (sidx < R) return false;
+        } else {
+            if (len <= 0) return false;  // tail (:71-79)
+            const double popped = pick(f, head);
+            head = (head + 1 == W) ? 0 : head + 1;
+            --len;
+            sum = __dsub_rn(sum, popped);
+            div = __ddiv_rn(1.0, (double)len);
+        }
+        out = __dmul_rn(sum, div);
+        put(o, slot, out);
+        return true;
+    }
+};
+
 template <int W>
 __global__ void __launch_bounds__(SL_THREADS)
 smooth_lanes_kernel(const SpecDesc *__restrict__ sd, int n_spec, int iters)
@@ -125,65 +187,8 @@ smooth_lanes_kernel(const SpecDesc *__restrict__ sd, int n_spec, int iters)
     for (int k = 0; k < SL_STAGES && k < in_tiles; ++k) issue_load(k);
 
     // ---- per-lane pass state
-    double f[W];
-#pragma unroll
-    for (int k = 0; k < W; ++k) f[k] = 0.0;
-    double o[W];  // outputs of the last W steps: slot (tau mod W) is read by the next lane W steps later
-#pragma unroll
-    for (int k = 0; k < W; ++k) o[k] = 0.0;
-    double sum = 0.0, div = 1.0, out = 0.0;
-    int len = 0, head = 0;
-    auto ring_get = [&](int slot) {
-        double v = f[0];
-#pragma unroll
-        for (int k = 1; k < W; ++k) v = (slot == k) ? f[k] : v;
-        return v;
-    };
-    auto hist_get = [&](int slot) {
-        double v = o[0];
-#pragma unroll
-        for (int k = 1; k < W; ++k) v = (slot == k) ? o[k] : v;
-        return v;
-    };
-    auto hist_set = [&](int slot, double v) {
-#pragma unroll
-        for (int k = 0; k < W; ++k) o[k] = (slot == k) ? v : o[k];
-    };
-    auto ring_set = [&](int slot, double v) {
-#pragma unroll
-        for (int k = 0; k < W; ++k) f[k] = (slot == k) ? v : f[k];
-    };
-
-    // one step of the state machine for any phase; `slot` = tau mod W.  Returns true when an
-    // output (index sidx - R) was produced into `out`.
-    auto general_step = [&](int sidx, int slot, double vin) -> bool {
-        if (!valid || sidx < 0 || sidx >= n + R) return false;
-        if (sidx < n) {
-            sum = __dadd_rn(sum, vin);
-            if (len == W) {  // circular_buffer.rs:35-40: pop the oldest, push into its slot
-                const double popped = ring_get(head);
-                ring_set(slot, vin);
-                head = (head + 1 == W) ? 0 : head + 1;
-                sum = __dsub_rn(sum, popped);
-            } else {
-                if (len == 0) head = slot;
-                ring_set(slot, vin);
-                ++len;
-                if (sidx >= R) div = __ddiv_rn(1.0, (double)len);  // main loop only (:66-68), not the preload
-            }
-            if (sidx < R) return false;
-            out = __dmul_rn(sum, div);
-            return true;
-        }
-        if (len <= 0) return false;  // tail (:71-79)
-        const double popped = ring_get(head);
-        head = (head + 1 == W) ? 0 : head + 1;
-        --len;
-        sum = __dsub_rn(sum, popped);
-        div = __ddiv_rn(1.0, (double)len);
-        out = __dmul_rn(sum, div);
-        return true;
-    };
+    PassState<W> ps;
+    ps.reset();
 
     for (int k = 0; k < tiles; ++k) {
         const int stage = k % SL_STAGES;
@@ -222,12 +227,12 @@ smooth_lanes_kernel(const SpecDesc *__restrict__ sd, int n_spec, int iters)
 #pragma unroll
                 for (int u = 0; u < W; ++u) {
                     const int j = g * W + u;
-                    const double up = __shfl_up_sync(0xffffffffu, o[u], 1);  // what lane p-1 emitted W steps ago
+                    const double up = __shfl_up_sync(0xffffffffu, ps.o[u], 1);  // what lane p-1 emitted W steps ago
                     const double vin = first ? cur[u] : up;
-                    sum = __dsub_rn(__dadd_rn(sum, vin), f[u]);
-                    f[u] = vin;
-                    o[u] = __dmul_rn(sum, div);
-                    if (last) { double *q = (j < L) ? pa : pb; q[j] = o[u]; }
+                    ps.sum = __dsub_rn(__dadd_rn(ps.sum, vin), ps.f[u]);
+                    ps.f[u] = vin;
+                    ps.o[u] = __dmul_rn(ps.sum, ps.div);
+                    if (last) { double *q = (j < L) ? pa : pb; q[j] = ps.o[u]; }
                 }
 #pragma unroll
                 for (int u = 0; u < W; ++u) cur[u] = nxt[u];
@@ -236,14 +241,13 @@ smooth_lanes_kernel(const SpecDesc *__restrict__ sd, int n_spec, int iters)
             for (int j = 0; j < T; ++j) {
                 const int tau = tau0 + j;
                 const int slot = tau % W;
-                double vin = __shfl_up_sync(0xffffffffu, hist_get(slot), 1);
+                double vin = __shfl_up_sync(0xffffffffu, PassState<W>::pick(ps.o, slot), 1);
                 if (first && tau < n) vin = irow[j];
                 const int sidx = tau - delay;
-                const bool emitted = general_step(sidx, slot, vin);
-                if (emitted) hist_set(slot, out);
+                const bool emitted = ps.step(valid, sidx, slot, vin, n);
                 if (last && emitted) {
-                    const int o = sidx - R;  // == tau - L
-                    orow(o / T)[o % T] = out;
+                    const int oi = sidx - R;  // == tau - L
+                    orow(oi / T)[oi % T] = ps.out;
                 }
             }
             // a fast tile may follow: its static addressing needs head == tau mod W, which holds for
@@ -255,6 +259,66 @@ smooth_lanes_kernel(const SpecDesc *__restrict__ sd, int n_spec, int iters)
     }
     if (tiles >= 1) flush_tile(tiles - 1);
     tma_bulk_wait_read<0>();
+}
+
+// ---------------------------------------------------------------------------------------------
+// All passes of ONE spectrum at once (Deconvoluter::optimize_settings, deconvoluter.rs:761-825):
+// the output of pass k of an I-pass smoothing IS the result of smoothing with k iterations, so one
+// run with I = `iters` lanes yields every iteration count 1..iters for this window.  Lane p writes
+// pass p's output stream to out + p * stride.  One warp; blockIdx.x selects the job.
+// ---------------------------------------------------------------------------------------------
+struct SmoothAllJob {
+    const double *y;   // raw intensities
+    double *out;       // iters rows of `stride` doubles
+    long long stride;
+    int n, iters, window;
+};
+
+template <int W>
+__device__ void smooth_all_passes_body(const SmoothAllJob &job)
+{
+    constexpr int R = W / 2;
+    const int lane = threadIdx.x;
+    const int n = job.n, iters = job.iters;
+    const bool valid = lane < iters;
+    const int delay = lane * (W + R);
+    double *__restrict__ row = job.out + (long long)lane * job.stride;
+    PassState<W> ps;
+    ps.reset();
+    const int steps = n + R + (iters - 1) * (W + R) + 1;
+    double chunk = (lane < n) ? job.y[lane] : 0.0;  // inputs tau0 .. tau0+31, one per lane (coalesced)
+    for (int tau0 = 0; tau0 < steps; tau0 += 32) {
+        const int nxt_i = tau0 + 32 + lane;
+        const double nxt = (nxt_i < n) ? job.y[nxt_i] : 0.0;  // prefetch the next 32 inputs
+#pragma unroll 1
+        for (int u = 0; u < 32; ++u) {
+            const int tau = tau0 + u;
+            const int slot = tau % W;
+            const double raw = __shfl_sync(0xffffffffu, chunk, u);
+            const double up = __shfl_up_sync(0xffffffffu, PassState<W>::pick(ps.o, slot), 1);
+            const double vin = (lane == 0) ? raw : up;
+            const int sidx = tau - delay;
+            if (ps.step(valid, sidx, slot, vin, n)) row[sidx - R] = ps.out;
+        }
+        chunk = nxt;
+    }
+}
+
+__global__ void __launch_bounds__(32)
+smooth_all_passes_kernel(const SmoothAllJob *__restrict__ jobs)
+{
+    const SmoothAllJob job = jobs[blockIdx.x];
+    switch (job.window) {
+    case 2: smooth_all_passes_body<2>(job); break;
+    case 3: smooth_all_passes_body<3>(job); break;
+    case 4: smooth_all_passes_body<4>(job); break;
+    case 5: smooth_all_passes_body<5>(job); break;
+    case 6: smooth_all_passes_body<6>(job); break;
+    case 7: smooth_all_passes_body<7>(job); break;
+    case 8: smooth_all_passes_body<8>(job); break;
+    case 9: smooth_all_passes_body<9>(job); break;
+    default: break;  // the host only submits windows 2..9
+    }
 }
 
 using SmoothLanesFn = void (*)(const SpecDesc *, int, int);

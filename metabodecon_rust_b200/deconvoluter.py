@@ -136,6 +136,21 @@ class Deconvoluter:
             if batch:
                 lib.mdb_batch_free(batch)
 
+    def optimize_settings(self, reference: Spectrum) -> float:
+        """`Deconvoluter::optimize_settings` (deconvoluter.rs:761-825, bindings/deconvoluter.rs:167-172):
+        810 deconvolutions of `reference` as one GPU batch; keeps the settings with the lowest MSE."""
+        if not isinstance(reference, Spectrum):
+            raise TypeError("expected a Spectrum")
+        view = _lib.SpectrumView()
+        view.chemical_shifts = reference.chemical_shifts.ctypes.data
+        view.intensities = reference.intensities.ctypes.data
+        view.len = reference.chemical_shifts.size
+        view.signal_boundaries[0], view.signal_boundaries[1] = reference.signal_boundaries
+        mse = C.c_double()
+        st = _lib.load().mdb_deconvoluter_optimize_settings(self._h, C.byref(view), _lib.MDB_MEM_HOST, C.byref(mse))
+        raise_for_status(st, _lib.last_error())
+        return float(mse.value)
+
     def deconvolute_spectrum(self, spectrum: Spectrum) -> Deconvolution:
         return self._run([spectrum])[0]
 

@@ -319,6 +319,20 @@ def deconvolute_spectrum(settings: Settings, x, y, sb, parallel: bool = False) -
                        i.n_after_ignore, (i.region_left, i.region_right), i.n_sfr, i.mean, i.sd)
 
 
+def optimize_settings(settings: Settings, x, y, sb):
+    """Deconvoluter::optimize_settings (deconvoluter.rs:761-825).  Returns
+    (status, (iterations, window, threshold, fit_iterations), best_mse, all 810 MSEs in iteration order)."""
+    x, y = _f64(x), _f64(y)
+    st, _keep = settings._c()
+    best = np.zeros(4, dtype=np.float64)
+    mse = C.c_double()
+    all_mse = np.zeros(810, dtype=np.float64)
+    lib().orc_optimize_settings.restype = C.c_int
+    status = lib().orc_optimize_settings(C.byref(st), _dp(x), _dp(y), C.c_size_t(y.size), C.c_double(sb[0]),
+                                         C.c_double(sb[1]), _dp(best), C.byref(mse), _dp(all_mse))
+    return status, (int(best[0]), int(best[1]), float(best[2]), int(best[3])), mse.value, all_mse
+
+
 def par_deconvolute_spectra(settings: Settings, x, ys, sb):
     """Batch form used as the CPU baseline: OpenMP over spectra (shared x, equal n).
 

@@ -644,6 +644,55 @@ int orc_par_deconvolute_spectra(const orc_settings *st, size_t n_spectra, const 
     return ORC_OK;
 }
 
+/*
+ * Deconvoluter::optimize_settings  deconvoluter.rs:761-825.  27 smoothing settings (iterations
+ * 2..=10 outer, window 3,5,7 inner) x 10 thresholds (5.0 + c*(8.0-5.0)/9.0) x 3 fit iteration
+ * counts (5, 10, 15); rayon over the smoothing settings -> OpenMP here.  The minimum is the FIRST
+ * smallest MSE in iteration order (Iterator::min_by).  best[4] = {iterations, window, threshold,
+ * fit iterations}.  Returns the first non-OK status in iteration order, ORC_PANIC for a NaN MSE.
+ */
+int orc_optimize_settings(const orc_settings *base, const double *x, const double *y, size_t n, double sb0,
+                          double sb1, double *best, double *best_mse, double *all_mse)
+{
+    enum { NS = 27, NT = 10, NF = 3 };
+    int status[NS * NT * NF];
+    double mse[NS * NT * NF];
+    size_t cap = n / 2 + 1;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int s = 0; s < NS; ++s) {
+        orc_lorentzian *lor = (orc_lorentzian *)malloc(cap * sizeof(orc_lorentzian));
+        for (int c = 0; c < NT; ++c)
+            for (int f = 0; f < NF; ++f) {
+                orc_settings st = *base;
+                st.smoothing_kind = ORC_SMOOTH_MOVING_AVERAGE;
+                st.smoothing_iterations = (size_t)(2 + s / 3);
+                st.smoothing_window = (size_t)(3 + 2 * (s % 3));
+                st.selection_kind = ORC_SELECT_NOISE_SCORE_FILTER;
+                st.threshold = 5.0 + (double)c * (8.0 - 5.0) / 9.0;
+                st.fitting_iterations = (size_t)(5 + 5 * f);
+                orc_result res;
+                orc_deconvolute_spectrum(&st, x, y, n, sb0, sb1, 0, lor, NULL, NULL, NULL, NULL, &res);
+                status[(s * NT + c) * NF + f] = res.status;
+                mse[(s * NT + c) * NF + f] = res.mse;
+            }
+        free(lor);
+    }
+    int best_i = 0;
+    for (int i = 0; i < NS * NT * NF; ++i) {
+        if (all_mse) all_mse[i] = mse[i];
+        if (status[i] != ORC_OK) return status[i];
+        if (!(mse[i] == mse[i])) return ORC_PANIC;
+        if (mse[i] < mse[best_i]) best_i = i;
+    }
+    int s = best_i / (NT * NF), c = (best_i / NF) % NT, f = best_i % NF;
+    best[0] = (double)(2 + s / 3);
+    best[1] = (double)(3 + 2 * (s % 3));
+    best[2] = 5.0 + (double)c * (8.0 - 5.0) / 9.0;
+    best[3] = (double)(5 + 5 * f);
+    *best_mse = mse[best_i];
+    return ORC_OK;
+}
+
 /* bench.py's reference arm runs under torchrun, which exports OMP_NUM_THREADS=1: let the caller
  * ask for all host cores explicitly. */
 void orc_set_num_threads(int n)

@@ -542,3 +542,47 @@ def test_device_resident_inputs_match_host_inputs():
             assert lib.mdb_batch_mse(batch, i) == host[i].mse
     finally:
         lib.mdb_batch_free(batch)
+
+
+# ------------------------------------------------------------------------------ optimize_settings
+def test_optimize_settings_sim_matches_oracle(golden_dir):
+    """deconvoluter.rs:761-825 on the reference's own example spectrum (sim_01, 3.339..3.553):
+    same optimum, same MSE bits, and the deconvoluter is left holding the optimal settings."""
+    sp = Spectrum.read_bruker(os.path.join(golden_dir, "bruker", "sim_01"), 10, 10, (3.339, 3.553))
+    status, best, want_mse, all_mse = O.optimize_settings(O.Settings(), sp.chemical_shifts, sp.intensities,
+                                                          sp.signal_boundaries)
+    assert status == O.OK
+    dec = Deconvoluter()
+    mse = dec.optimize_settings(sp)
+    assert_bit_equal([mse], [want_mse], "optimal mse")
+    assert dec.smoothing_settings() == {"method": "MovingAverage", "iterations": best[0], "windowSize": best[1]}
+    assert dec.selection_settings()["threshold"] == best[2]
+    assert dec.fitting_settings() == {"method": "Analytical", "iterations": best[3]}
+    # deconvoluting with the optimised settings reproduces that MSE
+    out = dec.deconvolute_spectrum(sp)
+    assert_bit_equal([out.mse], [want_mse], "mse with the optimal settings")
+
+
+def test_optimize_settings_blood_with_ignore_region(blood_arrays):
+    x, y = blood_arrays
+    sp = Spectrum(x, y, (-2.2, 11.8))
+    dec = Deconvoluter()
+    dec.add_ignore_region((4.7, 4.9))
+    mse = dec.optimize_settings(sp)
+    status, best, want_mse, _ = O.optimize_settings(O.Settings(ignore_regions=[(4.7, 4.9)]), x, y, sp.signal_boundaries)
+    assert status == O.OK
+    assert_bit_equal([mse], [want_mse], "blood optimal mse")
+    assert dec.smoothing_settings() == {"method": "MovingAverage", "iterations": best[0], "windowSize": best[1]}
+    assert dec.selection_settings()["threshold"] == best[2] and dec.fitting_settings()["iterations"] == best[3]
+    assert dec.ignore_regions() == [(4.7, 4.9)]
+
+
+def test_optimize_settings_error_leaves_settings_unchanged():
+    n = 4096
+    x = synth.axis(n)
+    flat = Spectrum(x, np.zeros(n), (-2.2, 11.8))
+    dec = Deconvoluter()
+    before = (dec.smoothing_settings(), dec.selection_settings(), dec.fitting_settings())
+    with pytest.raises(exceptions.NoPeaksDetected):
+        dec.optimize_settings(flat)
+    assert before == (dec.smoothing_settings(), dec.selection_settings(), dec.fitting_settings())

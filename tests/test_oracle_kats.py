@@ -192,3 +192,26 @@ def test_batch_baseline_matches_single(blood_arrays):
     st, lors, mse, nsel = O.par_deconvolute_spectra(O.Settings(), x, ys, (11.8, -2.2))
     one = O.deconvolute_spectrum(O.Settings(), x, y, (11.8, -2.2))
     assert st == O.OK and np.array_equal(lors[0].view(np.uint64), one.lorentzians.view(np.uint64)) and mse[0] == one.mse
+
+
+def test_optimize_settings_grid_and_argmin(sim_arrays):  # deconvoluter.rs:761-825
+    """The oracle's optimiser must agree with 810 individual oracle deconvolutions taken in the
+    reference's iteration order (smoothing outer, threshold, fit iterations inner; first minimum)."""
+    x, y = sim_arrays
+    sb = (3.55, 3.35) if x[0] > x[1] else (3.35, 3.55)
+    status, best, mse, all_mse = O.optimize_settings(O.Settings(), x, y, sb)
+    assert status == O.OK
+    want = []
+    for iterations in range(2, 11):
+        for window in (3, 5, 7):
+            for c in range(10):
+                for fit in (5, 10, 15):
+                    thr = 5.0 + float(c) * (8.0 - 5.0) / 9.0
+                    r = O.deconvolute_spectrum(O.Settings(smoothing_iterations=iterations, smoothing_window=window,
+                                                          threshold=thr, fitting_iterations=fit), x, y, sb)
+                    assert r.status == O.OK
+                    want.append(((iterations, window, thr, fit), r.mse))
+    assert [m for _, m in want] == all_mse.tolist()
+    k = int(np.argmin(all_mse))  # numpy argmin returns the first minimum, like Iterator::min_by
+    assert best == want[k][0] and mse == want[k][1]
+    assert 5.0 <= best[2] <= 8.0 and best[3] in (5, 10, 15)
