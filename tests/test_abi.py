@@ -31,6 +31,21 @@ def test_library_exports_every_declared_symbol():
     assert lib.mdb_abi_version() == 1
 
 
+def test_rust_sys_crate_declares_every_header_symbol():
+    """rust/metabodecon-sys cannot be compiled here (no cargo/rustc); at least keep its extern
+    block in step with the header: same symbol set, nothing missing, nothing invented."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with open(os.path.join(root, "include", "mdb200.h")) as fh:
+        header = fh.read()
+    with open(os.path.join(root, "rust", "metabodecon-sys", "src", "lib.rs")) as fh:
+        rust = fh.read()
+    declared = set(re.findall(r"\b(mdb_[a-z0-9_]+)\s*\(", header))
+    bound = set(re.findall(r"pub fn (mdb_[a-z0-9_]+)\s*\(", rust))
+    assert declared == bound, (sorted(declared - bound), sorted(bound - declared))
+    assert declared == {name for name, _, _ in _lib.SIGNATURES}
+
+
 def test_struct_layouts_match_the_header():
     assert C.sizeof(_lib.Lorentzian3) == 24        # lorentzian.rs:138-145: three f64
     assert C.sizeof(_lib.SmoothingSettings) == 24
