@@ -114,6 +114,9 @@ mdb_status mdb_host_free(void *ptr);
 mdb_status mdb_release_workspaces(void);
 /* Counters: kernels launched by this library in this process since the last reset. */
 uint64_t mdb_kernel_launch_count(void);
+/* Host->device and device->host bytes copied by this library since the last reset (e2e accounting). */
+void mdb_transfer_bytes(uint64_t *h2d, uint64_t *d2h);
+/* Resets the launch counter and the transfer byte counters. */
 void mdb_reset_kernel_launch_count(void);
 
 /* Optional per-kernel timing for roofline reports: CUDA events on the launching stream around

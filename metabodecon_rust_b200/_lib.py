@@ -72,6 +72,7 @@ SIGNATURES = [
     ("mdb_host_free", C.c_int, [_P]),
     ("mdb_release_workspaces", C.c_int, []),
     ("mdb_kernel_launch_count", C.c_uint64, []),
+    ("mdb_transfer_bytes", None, [C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     ("mdb_reset_kernel_launch_count", None, []),
     ("mdb_profile_enable", None, [C.c_int]),
     ("mdb_profile_reset", None, []),

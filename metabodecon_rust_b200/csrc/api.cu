@@ -30,6 +30,23 @@ using namespace mdb;
 // ---------------------------------------------------------------------------------------------
 static thread_local std::string g_last_error;
 static std::atomic<uint64_t> g_launches{0};
+static std::atomic<uint64_t> g_h2d_bytes{0}, g_d2h_bytes{0};  // host<->device bytes moved by this library
+
+static void count_transfer(size_t bytes, cudaMemcpyKind kind)
+{
+    if (kind == cudaMemcpyHostToDevice) g_h2d_bytes += bytes;
+    else if (kind == cudaMemcpyDeviceToHost) g_d2h_bytes += bytes;
+}
+static cudaError_t counted_memcpy_async(void *dst, const void *src, size_t bytes, cudaMemcpyKind kind, cudaStream_t stream)
+{
+    count_transfer(bytes, kind);
+    return cudaMemcpyAsync(dst, src, bytes, kind, stream);
+}
+static cudaError_t counted_memcpy(void *dst, const void *src, size_t bytes, cudaMemcpyKind kind)
+{
+    count_transfer(bytes, kind);
+    return cudaMemcpy(dst, src, bytes, kind);
+}
 
 static mdb_status fail(mdb_status st, const std::string &msg)
 {
@@ -111,9 +128,19 @@ extern "C" mdb_status mdb_profile_read(int kernel, double *ms, uint64_t *launche
 }
 
 extern "C" uint32_t mdb_abi_version(void) { return MDB200_ABI_VERSION; }
+extern "C" void mdb_transfer_bytes(uint64_t *h2d, uint64_t *d2h)
+{
+    if (h2d) *h2d = g_h2d_bytes.load();
+    if (d2h) *d2h = g_d2h_bytes.load();
+}
 extern "C" const char *mdb_last_error_message(void) { return g_last_error.c_str(); }
 extern "C" uint64_t mdb_kernel_launch_count(void) { return g_launches.load(); }
-extern "C" void mdb_reset_kernel_launch_count(void) { g_launches.store(0); }
+extern "C" void mdb_reset_kernel_launch_count(void)
+{
+    g_launches.store(0);
+    g_h2d_bytes.store(0);
+    g_d2h_bytes.store(0);
+}
 
 extern "C" int mdb_device_count(void)
 {
@@ -593,7 +620,8 @@ struct Chunk {
     long long p_total = 0;             // selected peaks in the chunk
     long long res_total = 0;
     int max_tiles = 0, max_peaks = 0, max_seg_len = 0;
-    bool stage_b_launched = false;
+    bool stage_b_launched = false, finished = false;
+    double est_evals = 0.0;            // Lorentzian evaluations of this chunk's fit + MSE kernels (from the counts)
     std::vector<ProfSpan> spans;       // per-kernel timing, resolved in finish_chunk
 };
 
@@ -734,9 +762,9 @@ static mdb_status stage_a(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
         for (size_t q = 0; q < h.ig.size(); ++q) h_ig[ig_off[s] + q] = h.ig[q];
     }
     std::memcpy(ws.h_desc.p, ck.desc.data(), S * sizeof(SpecDesc));
-    CUDA_TRY(cudaMemcpyAsync(ws.desc.p, ws.h_desc.p, S * sizeof(SpecDesc), cudaMemcpyHostToDevice, ws.stream));
+    CUDA_TRY(counted_memcpy_async(ws.desc.p, ws.h_desc.p, S * sizeof(SpecDesc), cudaMemcpyHostToDevice, ws.stream));
     if (ig_elems)
-        CUDA_TRY(cudaMemcpyAsync(ws.ig.p, ws.h_ig.p, ig_elems * 4, cudaMemcpyHostToDevice, ws.stream));
+        CUDA_TRY(counted_memcpy_async(ws.ig.p, ws.h_ig.p, ig_elems * 4, cudaMemcpyHostToDevice, ws.stream));
 
     // ---- inputs to the device (rows that are adjacent on the host and on the device go as one copy)
     double *y_dst = skip_smoothing_input_is_smoothed ? ws.ys.as<double>() : ws.y.as<double>();
@@ -745,7 +773,7 @@ static mdb_status stage_a(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
             size_t n = 0;
             for (size_t s = 0; s < S; ++s)
                 if (hs[ck.first + s].x == kv.first) { n = hs[ck.first + s].n; break; }
-            CUDA_TRY(cudaMemcpyAsync(ws.x.as<double>() + kv.second, kv.first, n * 8, cudaMemcpyHostToDevice, ws.stream));
+            CUDA_TRY(counted_memcpy_async(ws.x.as<double>() + kv.second, kv.first, n * 8, cudaMemcpyHostToDevice, ws.stream));
         }
         size_t s = 0;
         while (s < S) {
@@ -757,12 +785,12 @@ static mdb_status stage_a(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
                 if (hp.n % 16 == 0 && hn.y == hp.y + hp.n) { bytes += hn.n * 8; ++e; }
                 else break;
             }
-            CUDA_TRY(cudaMemcpyAsync(y_dst + y_off[s], h0.y, bytes, cudaMemcpyHostToDevice, ws.stream));
+            CUDA_TRY(counted_memcpy_async(y_dst + y_off[s], h0.y, bytes, cudaMemcpyHostToDevice, ws.stream));
             s = e;
         }
     } else if (skip_smoothing_input_is_smoothed) {
         for (size_t s = 0; s < S; ++s)
-            CUDA_TRY(cudaMemcpyAsync(y_dst + y_off[s], hs[ck.first + s].y, hs[ck.first + s].n * 8,
+            CUDA_TRY(counted_memcpy_async(y_dst + y_off[s], hs[ck.first + s].y, hs[ck.first + s].n * 8,
                                      cudaMemcpyDeviceToDevice, ws.stream));
     }
 
@@ -775,7 +803,7 @@ static mdb_status stage_a(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
             if (sst != MDB_OK) return sst;
         } else {  // Identity (smoothing/identity.rs): the smoothed copy is the input itself
             for (size_t s = 0; s < S; ++s)
-                CUDA_TRY(cudaMemcpyAsync(ck.desc[s].ys, ck.desc[s].y, (size_t)ck.desc[s].n * 8,
+                CUDA_TRY(counted_memcpy_async(ck.desc[s].ys, ck.desc[s].y, (size_t)ck.desc[s].n * 8,
                                          cudaMemcpyDeviceToDevice, ws.stream));
         }
     }
@@ -802,7 +830,7 @@ static mdb_status stage_a(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
         LAUNCH_CHECK();
         prof_end(&ck.spans, ws.stream, (double)S);
     }
-    CUDA_TRY(cudaMemcpyAsync(ws.h_sel_out.p, ws.sel_out.p, S * sizeof(SelectOut), cudaMemcpyDeviceToHost, ws.stream));
+    CUDA_TRY(counted_memcpy_async(ws.h_sel_out.p, ws.sel_out.p, S * sizeof(SelectOut), cudaMemcpyDeviceToHost, ws.stream));
     CUDA_TRY(cudaEventRecord(ws.ev_a, ws.stream));
     return MDB_OK;
 }
@@ -830,6 +858,7 @@ static mdb_status stage_b(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
     ck.fdesc.assign(S, FitDesc{});
     ck.segs.clear();
     ck.p_total = 0;
+    ck.est_evals = 0.0;
     ck.res_total = 0;
     ck.max_peaks = 0;
     ck.max_seg_len = 0;
@@ -855,6 +884,11 @@ static mdb_status stage_b(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
                 ++f.seg_cnt;
             }
         }
+        {
+            double seg_pts = 0.0;
+            if (r.status == MDB_OK) for (auto &rg : h.ranges) seg_pts += (double)(rg.second - rg.first);
+            ck.est_evals += (double)f.n_peaks * (3.0 * (double)f.n_iters * (double)f.n_peaks + seg_pts);
+        }
         ck.p_total += (f.n_peaks + 1) & ~1;  // even offsets: every parameter block stays 16-byte aligned (TMA bulk copies)
         ck.max_peaks = std::max(ck.max_peaks, f.n_peaks);
     }
@@ -877,10 +911,10 @@ static mdb_status stage_b(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
     CUDA_TRY(ws.h_n_kept.ensure(S * 4));
     CUDA_TRY(ws.h_mse.ensure(S * 8));
     std::memcpy(ws.h_fdesc.p, ck.fdesc.data(), S * sizeof(FitDesc));
-    CUDA_TRY(cudaMemcpyAsync(ws.fdesc.p, ws.h_fdesc.p, S * sizeof(FitDesc), cudaMemcpyHostToDevice, ws.stream));
+    CUDA_TRY(counted_memcpy_async(ws.fdesc.p, ws.h_fdesc.p, S * sizeof(FitDesc), cudaMemcpyHostToDevice, ws.stream));
     if (n_seg) {
         std::memcpy(ws.h_segs.p, ck.segs.data(), n_seg * sizeof(Segment));
-        CUDA_TRY(cudaMemcpyAsync(ws.segs.p, ws.h_segs.p, n_seg * sizeof(Segment), cudaMemcpyHostToDevice, ws.stream));
+        CUDA_TRY(counted_memcpy_async(ws.segs.p, ws.h_segs.p, n_seg * sizeof(Segment), cudaMemcpyHostToDevice, ws.stream));
     }
     const SpecDesc *d_desc = ws.desc.as<SpecDesc>();
     const FitDesc *d_fd = ws.fdesc.as<FitDesc>();
@@ -897,7 +931,7 @@ static mdb_status stage_b(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
         // trace is a single-spectrum facility (mdb_stage_fit): p_total carries alignment padding, n_peaks does not
         const size_t n_trace = (size_t)ck.fdesc[0].n_peaks;
         if (trace) {
-            CUDA_TRY(cudaMemcpyAsync(trace, st.pa, n_trace * 24, cudaMemcpyDeviceToHost, ws.stream));
+            CUDA_TRY(counted_memcpy_async(trace, st.pa, n_trace * 24, cudaMemcpyDeviceToHost, ws.stream));
         }
         for (int it = 0; it < iters; ++it) {
             double evals = 0.0;  // E_fit of this pass = sum of 3 * P_s^2 over the spectra still iterating
@@ -908,7 +942,7 @@ static mdb_status stage_b(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
             LAUNCH_CHECK();
             prof_end(&ck.spans, ws.stream, evals);
             if (trace)
-                CUDA_TRY(cudaMemcpyAsync(trace + (size_t)(it + 1) * n_trace, (it & 1) ? st.pa : st.pb, n_trace * 24,
+                CUDA_TRY(counted_memcpy_async(trace + (size_t)(it + 1) * n_trace, (it & 1) ? st.pa : st.pb, n_trace * 24,
                                          cudaMemcpyDeviceToHost, ws.stream));
         }
     }
@@ -937,12 +971,12 @@ static mdb_status stage_b(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
                                                                                   ws.resid.as<double>(), ws.mse.as<double>(), (int)S);
         LAUNCH_CHECK();
         prof_end(&ck.spans, ws.stream, 8.0 * (double)ck.res_total);
-        CUDA_TRY(cudaMemcpyAsync(ws.h_mse.p, ws.mse.p, S * 8, cudaMemcpyDeviceToHost, ws.stream));
+        CUDA_TRY(counted_memcpy_async(ws.h_mse.p, ws.mse.p, S * 8, cudaMemcpyDeviceToHost, ws.stream));
     }
-    CUDA_TRY(cudaMemcpyAsync(ws.h_n_kept.p, ws.n_kept.p, S * 4, cudaMemcpyDeviceToHost, ws.stream));
+    CUDA_TRY(counted_memcpy_async(ws.h_n_kept.p, ws.n_kept.p, S * 4, cudaMemcpyDeviceToHost, ws.stream));
     if (ck.p_total > 0) {
-        CUDA_TRY(cudaMemcpyAsync(ws.h_lor.p, ws.lor.p, (size_t)ck.p_total * 24, cudaMemcpyDeviceToHost, ws.stream));
-        CUDA_TRY(cudaMemcpyAsync(ws.h_peaks.p, ws.peaks_dense.p, (size_t)ck.p_total * 12, cudaMemcpyDeviceToHost, ws.stream));
+        CUDA_TRY(counted_memcpy_async(ws.h_lor.p, ws.lor.p, (size_t)ck.p_total * 24, cudaMemcpyDeviceToHost, ws.stream));
+        CUDA_TRY(counted_memcpy_async(ws.h_peaks.p, ws.peaks_dense.p, (size_t)ck.p_total * 12, cudaMemcpyDeviceToHost, ws.stream));
     }
     CUDA_TRY(cudaEventRecord(ws.ev_b, ws.stream));
     ck.stage_b_launched = true;
@@ -973,6 +1007,7 @@ static mdb_status finish_chunk(Chunk &ck, std::vector<SpecResult> &results, bool
         r.peaks.assign(pk + 3 * f.off, pk + 3 * (f.off + f.n_peaks));
         r.mse = with_mse ? mse[s] : 0.0;
     }
+    ck.finished = true;
     return MDB_OK;
 }
 
@@ -982,10 +1017,14 @@ static size_t chunk_size_for(const std::vector<HostSpec> &hs)
     for (auto &h : hs) max_n = std::max(max_n, h.n);
     const char *env = std::getenv("MDB_CHUNK_SPECTRA");
     if (env && std::atoi(env) > 0) return (size_t)std::atoi(env);
+    // About 2^23 points per chunk (64 spectra of 2^17 points): small enough that eight chunks in
+    // flight keep every SM busy through each other's kernel tails and host round trips, large
+    // enough that a fit-refinement launch still fills the GPU (measured: gpurun_out/depth_sweep*.log).
     const size_t per_spec = 48 * max_n + 4096;          // device bytes per spectrum
     const size_t budget = (size_t)1536 << 20;           // per workspace
-    size_t c = budget / per_spec;
-    c = std::max<size_t>(1, std::min<size_t>(c, 512));
+    size_t c = std::min(budget / per_spec, ((size_t)1 << 23) / std::max<size_t>(max_n, 1));
+    c = std::max<size_t>(16, std::min<size_t>(c, 512));
+    c = std::max<size_t>(1, std::min(c, budget / per_spec));
     return c;
 }
 
@@ -1013,7 +1052,7 @@ static mdb_status build_host_specs(const mdb_deconvoluter &dc, const mdb_spectru
         if (it == x01.end()) {
             double two[2];
             if (memory == MDB_MEM_HOST) { two[0] = h.x[0]; two[1] = h.x[1]; }
-            else CUDA_TRY(cudaMemcpy(two, h.x, 16, cudaMemcpyDeviceToHost));
+            else CUDA_TRY(counted_memcpy(two, h.x, 16, cudaMemcpyDeviceToHost));
             it = x01.emplace(h.x, std::make_pair(two[0], two[1])).first;
         }
         h.x0 = it->second.first;
@@ -1025,53 +1064,85 @@ static mdb_status build_host_specs(const mdb_deconvoluter &dc, const mdb_spectru
     return MDB_OK;
 }
 
-// The chunked pipeline over a prepared list of spectra.  Three workspaces in flight: stage A of
-// chunk k+1 is queued before the host waits for the counts of chunk k, and chunk k-1 is unpacked
-// while chunk k runs its fit / MSE kernels.
+// The chunked pipeline over a prepared list of spectra.  Up to eight workspaces (one stream each)
+// in flight: stage A of chunk k+1 is queued before the host waits for the counts of chunk k, and
+// older chunks are unpacked while the younger ones run their fit / MSE kernels.
 static mdb_status run_pipeline(const mdb_deconvoluter &dc, const std::vector<HostSpec> &hs, int memory,
                                std::vector<SpecResult> &results)
 {
     const size_t n_spectra = hs.size();
     mdb_status st = MDB_OK;
-    // Three workspaces in flight: stage A of chunk k+1 is queued before the host waits for the
-    // counts of chunk k, and chunk k-1 is unpacked while chunk k runs its fit / MSE kernels.
-    const size_t csz_max = chunk_size_for(hs);
-    const size_t n_chunks = (n_spectra + csz_max - 1) / csz_max;
-    const size_t csz = (n_spectra + n_chunks - 1) / n_chunks;  // equal-sized chunks, no straggler
-    size_t depth = 3;
+    size_t depth = 8;
     if (const char *env = std::getenv("MDB_PIPELINE_DEPTH"))
-        if (std::atoi(env) >= 1) depth = (size_t)std::min(std::atoi(env), 8);
-    const size_t n_ws = std::min<size_t>(depth, n_chunks);
-    std::vector<Workspace *> wss(n_ws, nullptr);
+        if (std::atoi(env) >= 1) depth = (size_t)std::min(std::atoi(env), 32);
+    // Chunk size: starts at chunk_size_for() and, unless pinned by MDB_CHUNK_SPECTRA, is re-derived
+    // from the first chunk's selected-peak counts so that a chunk carries about TARGET Lorentzian
+    // evaluations (~12 ms of FP64 work): many-peak spectra get small chunks (fine-grained overlap
+    // of kernel tails across streams), few-peak spectra get large ones (launch and smoothing
+    // latency amortised).  Measured in gpurun_out/depth_sweep*.log.
+    const double TARGET_EVALS = 1.8e10;
+    const bool pinned_size = std::getenv("MDB_CHUNK_SPECTRA") && std::atoi(std::getenv("MDB_CHUNK_SPECTRA")) > 0;
+    const size_t csz_first = chunk_size_for(hs);
+    size_t csz = csz_first;
+    std::vector<Workspace *> wss;
     auto cleanup = [&]() {
         for (Workspace *w : wss)
             if (w) { cudaStreamSynchronize(w->stream); release_workspace(w); }
     };
-    for (size_t i = 0; i < n_ws; ++i)
-        if ((st = acquire_workspace(&wss[i])) != MDB_OK) { cleanup(); return st; }
-    std::vector<Chunk> chunks(n_chunks);
-    for (size_t k = 0; k < n_chunks; ++k) {
-        chunks[k].ws = wss[k % n_ws];
-        chunks[k].first = k * csz;
-        chunks[k].count = std::min(csz, n_spectra - k * csz);
-    }
+    std::vector<Chunk> chunks;
+    chunks.reserve(n_spectra / 16 + 2);
+    size_t next_first = 0;
+    auto make_chunk = [&]() -> mdb_status {  // appends the next chunk; its workspace is that of chunk k - depth
+        Chunk ck;
+        const size_t k = chunks.size();
+        if (k < depth) {
+            Workspace *w = nullptr;
+            mdb_status s2 = acquire_workspace(&w);
+            if (s2 != MDB_OK) return s2;
+            wss.push_back(w);
+        }
+        ck.ws = wss[k % depth];
+        ck.first = next_first;
+        size_t count = std::min(csz, n_spectra - next_first);
+        if (n_spectra - next_first - count < csz / 4) count = n_spectra - next_first;  // no tiny straggler chunk
+        ck.count = count;
+        next_first += count;
+        chunks.push_back(std::move(ck));
+        return MDB_OK;
+    };
+    auto retune = [&](const Chunk &ck) {
+        if (pinned_size || ck.count == 0 || ck.est_evals <= 0.0) return;
+        const double per_spec = ck.est_evals / (double)ck.count;
+        const size_t want = (size_t)std::max(1.0, TARGET_EVALS / per_spec);
+        size_t max_n = 0;
+        for (auto &h : hs) max_n = std::max(max_n, h.n);
+        const size_t mem_cap = std::max<size_t>(1, ((size_t)1536 << 20) / (48 * max_n + 4096));
+        csz = std::max<size_t>(std::min<size_t>(32, mem_cap), std::min({want, (size_t)512, mem_cap}));
+    };
+    if ((st = make_chunk()) != MDB_OK) { cleanup(); return st; }
     st = stage_a(chunks[0], hs, dc, memory, false);
-    for (size_t k = 0; st == MDB_OK && k < n_chunks; ++k) {
-        if (n_ws == 1) {  // strictly serial (used for per-kernel profiling): A(k) B(k) finish(k) A(k+1)
+    for (size_t k = 0; st == MDB_OK && k < chunks.size(); ++k) {
+        if (depth == 1) {  // strictly serial (used for per-kernel profiling): A(k) B(k) finish(k) A(k+1)
             st = stage_b(chunks[k], hs, dc, results, true, nullptr);
             if (st == MDB_OK) st = finish_chunk(chunks[k], results, true);
-            if (st == MDB_OK && k + 1 < n_chunks) st = stage_a(chunks[k + 1], hs, dc, memory, false);
+            if (st == MDB_OK && k == 0) retune(chunks[0]);
+            if (st == MDB_OK && next_first < n_spectra) {
+                st = make_chunk();
+                if (st == MDB_OK) st = stage_a(chunks[k + 1], hs, dc, memory, false);
+            }
             continue;
         }
-        if (k + 1 < n_chunks) {
-            if (k + 1 >= n_ws) st = finish_chunk(chunks[k + 1 - n_ws], results, true);  // frees that workspace
+        if (next_first < n_spectra) {
+            if (k + 1 >= depth) st = finish_chunk(chunks[k + 1 - depth], results, true);  // frees that workspace
+            if (st == MDB_OK) st = make_chunk();
             if (st == MDB_OK) st = stage_a(chunks[k + 1], hs, dc, memory, false);
         }
         if (st == MDB_OK) st = stage_b(chunks[k], hs, dc, results, true, nullptr);
+        if (st == MDB_OK && k == 0) retune(chunks[0]);
     }
-    if (n_ws > 1)
-        for (size_t k = (n_chunks >= n_ws ? n_chunks - n_ws : 0); st == MDB_OK && k < n_chunks; ++k)
-            if (chunks[k].stage_b_launched) st = finish_chunk(chunks[k], results, true);
+    if (depth > 1)
+        for (size_t k = (chunks.size() >= depth ? chunks.size() - depth : 0); st == MDB_OK && k < chunks.size(); ++k)
+            if (chunks[k].stage_b_launched && !chunks[k].finished) st = finish_chunk(chunks[k], results, true);
     cleanup();
     return st;
 }
@@ -1164,8 +1235,8 @@ extern "C" mdb_status mdb_deconvoluter_optimize_settings(mdb_deconvoluter *d, co
     if (memory == MDB_MEM_HOST) {
         CUDA_TRY(xb.ensure(stride * 8));
         CUDA_TRY(yb.ensure(stride * 8));
-        CUDA_TRY(cudaMemcpy(xb.p, spectrum->chemical_shifts, n * 8, cudaMemcpyHostToDevice));
-        CUDA_TRY(cudaMemcpy(yb.p, spectrum->intensities, n * 8, cudaMemcpyHostToDevice));
+        CUDA_TRY(counted_memcpy(xb.p, spectrum->chemical_shifts, n * 8, cudaMemcpyHostToDevice));
+        CUDA_TRY(counted_memcpy(yb.p, spectrum->intensities, n * 8, cudaMemcpyHostToDevice));
         dx = xb.as<double>();
         dy = yb.as<double>();
     }
@@ -1178,7 +1249,7 @@ extern "C" mdb_status mdb_deconvoluter_optimize_settings(mdb_deconvoluter *d, co
         jobs[w].iters = max_iters;
         jobs[w].window = windows[w];
     }
-    CUDA_TRY(cudaMemcpy(jobb.p, jobs, sizeof(jobs), cudaMemcpyHostToDevice));
+    CUDA_TRY(counted_memcpy(jobb.p, jobs, sizeof(jobs), cudaMemcpyHostToDevice));
     smooth_all_passes_kernel<<<3, 32, 0, stream>>>(jobb.as<SmoothAllJob>());
     LAUNCH_CHECK();
     CUDA_TRY(cudaDeviceSynchronize());
@@ -1243,13 +1314,13 @@ extern "C" mdb_status mdb_superposition_vec(const double *x, size_t n, const mdb
     if (memory == MDB_MEM_HOST) {
         CUDA_TRY(ws->x.ensure(n * 8));
         CUDA_TRY(ws->ys.ensure(n * 8));
-        CUDA_TRY(cudaMemcpyAsync(ws->x.p, x, n * 8, cudaMemcpyHostToDevice, ws->stream));
+        CUDA_TRY(counted_memcpy_async(ws->x.p, x, n * 8, cudaMemcpyHostToDevice, ws->stream));
         dx = ws->x.as<double>();
         dout = ws->ys.as<double>();
     }
     if (memory == MDB_MEM_HOST || ((uintptr_t)lor & 15) != 0) {  // the kernel's bulk copies need 16-byte alignment
         CUDA_TRY(ws->lor.ensure(std::max<size_t>(p, 1) * 24));
-        if (p) CUDA_TRY(cudaMemcpyAsync(ws->lor.p, lor, p * 24, memory == MDB_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, ws->stream));
+        if (p) CUDA_TRY(counted_memcpy_async(ws->lor.p, lor, p * 24, memory == MDB_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, ws->stream));
         dl = ws->lor.as<double>();
     }
     const size_t blocks8 = (n + (size_t)SUP_THREADS * 8 - 1) / ((size_t)SUP_THREADS * 8);
@@ -1264,7 +1335,7 @@ extern "C" mdb_status mdb_superposition_vec(const double *x, size_t n, const mdb
                                                                       nullptr, nullptr, nullptr);
     LAUNCH_CHECK();
     prof_end(&spans, ws->stream, (double)n * (double)p);
-    if (memory == MDB_MEM_HOST) CUDA_TRY(cudaMemcpyAsync(out, dout, n * 8, cudaMemcpyDeviceToHost, ws->stream));
+    if (memory == MDB_MEM_HOST) CUDA_TRY(counted_memcpy_async(out, dout, n * 8, cudaMemcpyDeviceToHost, ws->stream));
     CUDA_TRY(cudaStreamSynchronize(ws->stream));
     prof_resolve(&spans);
     return MDB_OK;
@@ -1295,14 +1366,14 @@ extern "C" mdb_status mdb_stage_smooth(const double *values, size_t n, uint64_t 
     d.ys = ws->ys.as<double>();
     d.tmp = ws->tmp.as<double>();
     d.n = (int)n;
-    CUDA_TRY(cudaMemcpyAsync(ws->y.p, values, n * 8, cudaMemcpyHostToDevice, ws->stream));
-    CUDA_TRY(cudaMemcpyAsync(ws->desc.p, &d, sizeof(d), cudaMemcpyHostToDevice, ws->stream));
+    CUDA_TRY(counted_memcpy_async(ws->y.p, values, n * 8, cudaMemcpyHostToDevice, ws->stream));
+    CUDA_TRY(counted_memcpy_async(ws->desc.p, &d, sizeof(d), cudaMemcpyHostToDevice, ws->stream));
     {
         std::vector<SpecDesc> descs(1, d);
         if ((st = launch_smooth(ws->stream, ws->desc.as<SpecDesc>(), descs, (int)iterations, (int)window, nullptr)) != MDB_OK)
             return st;
     }
-    CUDA_TRY(cudaMemcpyAsync(out, ws->ys.p, n * 8, cudaMemcpyDeviceToHost, ws->stream));
+    CUDA_TRY(counted_memcpy_async(out, ws->ys.p, n * 8, cudaMemcpyDeviceToHost, ws->stream));
     CUDA_TRY(cudaStreamSynchronize(ws->stream));
     return MDB_OK;
 }
@@ -1350,15 +1421,15 @@ extern "C" mdb_status mdb_stage_detect(const double *smoothed, size_t n, int32_t
     const SpecDesc &d = ck.desc[0];
     std::vector<int> tile_cnt(d.n_tiles);
     CUDA_TRY(cudaStreamSynchronize(ws->stream));
-    CUDA_TRY(cudaMemcpy(tile_cnt.data(), d.tile_cnt, (size_t)d.n_tiles * 4, cudaMemcpyDeviceToHost));
+    CUDA_TRY(counted_memcpy(tile_cnt.data(), d.tile_cnt, (size_t)d.n_tiles * 4, cudaMemcpyDeviceToHost));
     std::vector<int> pk(3 * (size_t)DETECT_CAP);
     std::vector<double> sc(DETECT_CAP);
     size_t k = 0;
     for (int t = 0; t < d.n_tiles; ++t) {
         const int c = tile_cnt[t];
         if (c == 0) continue;
-        CUDA_TRY(cudaMemcpy(pk.data(), d.pk + 3 * (size_t)t * DETECT_CAP, (size_t)c * 12, cudaMemcpyDeviceToHost));
-        CUDA_TRY(cudaMemcpy(sc.data(), d.sc + (size_t)t * DETECT_CAP, (size_t)c * 8, cudaMemcpyDeviceToHost));
+        CUDA_TRY(counted_memcpy(pk.data(), d.pk + 3 * (size_t)t * DETECT_CAP, (size_t)c * 12, cudaMemcpyDeviceToHost));
+        CUDA_TRY(counted_memcpy(sc.data(), d.sc + (size_t)t * DETECT_CAP, (size_t)c * 8, cudaMemcpyDeviceToHost));
         for (int i = 0; i < c; ++i, ++k) {
             if (k < cap) {
                 peaks[3 * k] = pk[3 * i]; peaks[3 * k + 1] = pk[3 * i + 1]; peaks[3 * k + 2] = pk[3 * i + 2];
@@ -1392,7 +1463,7 @@ extern "C" mdb_status mdb_stage_select(const mdb_deconvoluter *dc, const double 
     if (mean_sd) { mean_sd[0] = so.mean; mean_sd[1] = so.sd; }
     if (so.status != MDB_OK) return fail((mdb_status)so.status, status_text(so.status));
     const size_t ncopy = std::min<size_t>(cap, (size_t)so.n_selected);
-    if (ncopy) CUDA_TRY(cudaMemcpy(peaks, ck.desc[0].sel, ncopy * 12, cudaMemcpyDeviceToHost));
+    if (ncopy) CUDA_TRY(counted_memcpy(peaks, ck.desc[0].sel, ncopy * 12, cudaMemcpyDeviceToHost));
     return MDB_OK;
 }
 
@@ -1434,10 +1505,10 @@ extern "C" mdb_status mdb_stage_fit(const double *x, const double *y, size_t n, 
     d.sel = ws->sel.as<int>();
     d.n = (int)n;
     ck.desc.assign(1, d);
-    CUDA_TRY(cudaMemcpyAsync(ws->x.p, x, n * 8, cudaMemcpyHostToDevice, ws->stream));
-    CUDA_TRY(cudaMemcpyAsync(ws->y.p, y, n * 8, cudaMemcpyHostToDevice, ws->stream));
-    CUDA_TRY(cudaMemcpyAsync(ws->sel.p, peaks, n_peaks * 12, cudaMemcpyHostToDevice, ws->stream));
-    CUDA_TRY(cudaMemcpyAsync(ws->desc.p, &d, sizeof(d), cudaMemcpyHostToDevice, ws->stream));
+    CUDA_TRY(counted_memcpy_async(ws->x.p, x, n * 8, cudaMemcpyHostToDevice, ws->stream));
+    CUDA_TRY(counted_memcpy_async(ws->y.p, y, n * 8, cudaMemcpyHostToDevice, ws->stream));
+    CUDA_TRY(counted_memcpy_async(ws->sel.p, peaks, n_peaks * 12, cudaMemcpyHostToDevice, ws->stream));
+    CUDA_TRY(counted_memcpy_async(ws->desc.p, &d, sizeof(d), cudaMemcpyHostToDevice, ws->stream));
     SelectOut so{};
     so.status = MDB_OK;
     so.n_selected = (int)n_peaks;

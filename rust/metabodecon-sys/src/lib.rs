@@ -91,6 +91,7 @@ extern "C" {
     pub fn mdb_host_free(ptr: *mut c_void) -> mdb_status;
     pub fn mdb_release_workspaces() -> mdb_status;
     pub fn mdb_kernel_launch_count() -> u64;
+    pub fn mdb_transfer_bytes(h2d: *mut u64, d2h: *mut u64);
     pub fn mdb_reset_kernel_launch_count();
     pub fn mdb_profile_enable(on: c_int);
     pub fn mdb_profile_reset();
