@@ -661,13 +661,13 @@ static mdb_status launch_smooth(cudaStream_t stream, const SpecDesc *d_desc, con
         pts += (double)d.n;
         aligned = aligned && (((uintptr_t)d.y & 15) == 0) && (((uintptr_t)d.ys & 15) == 0);
     }
-    int tile = 0;
-    SmoothLanesFn fn = smooth_lanes_lookup(window, iters, &tile);
+    int stride = 0;
+    SmoothLanesFn fn = smooth_lanes_lookup(window, iters, &stride);
     const char *force = std::getenv("MDB_SMOOTH_GENERIC");
     prof_begin(spans, MDB_KERNEL_SMOOTH, stream);
     if (fn && aligned && !(force && force[0] == '1')) {
         const int groups = 32 / iters;  // spectra per warp: one lane per (spectrum, pass)
-        const size_t smem = smooth_lanes_smem_bytes(tile, groups);
+        const size_t smem = smooth_lanes_smem_bytes(stride, groups);
         CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         fn<<<(unsigned)((S + groups - 1) / groups), SL_THREADS, smem, stream>>>(d_desc, (int)S, iters);
         LAUNCH_CHECK();

@@ -49,15 +49,21 @@ constexpr int SL_STAGES = 4;    // input tiles in flight per warp
 constexpr int SL_OSTAGES = 3;   // output tiles in the ring
 constexpr int SL_THREADS = 32;  // one warp per CTA
 
-// tile length: a multiple of W (static ring slots) and even (16-byte bulk copies), at most 112
-template <int W> struct SmoothTile {
-    static constexpr int Q = 112 / W;
+// Tile length: a multiple of W (static ring slots) and even (16-byte bulk copies).  BIG tiles
+// (about 224 points) amortise the per-tile costs (mbarrier wait, one bulk copy per row each way,
+// proxy fence) when a warp holds at most 10 spectra (3 or more passes); the small tile (about
+// 112) keeps the 32-spectra case (1 pass) inside the shared-memory limit.
+template <int W, bool BIG> struct SmoothTile {
+    static constexpr int Q = (BIG ? 224 : 112) / W;
     static constexpr int T = W * ((W % 2) ? (Q & ~1) : Q);
+    // row stride in doubles: even (16-byte rows for the bulk copies) with an odd half, so that the
+    // rows of the spectra sharing a warp start in different shared-memory banks
+    static constexpr int STRIDE = ((T + 2) / 2) % 2 ? T + 2 : T + 4;
 };
 
-inline size_t smooth_lanes_smem_bytes(int tile, int groups)
+inline size_t smooth_lanes_smem_bytes(int stride, int groups)
 {
-    return (size_t)(SL_STAGES + SL_OSTAGES) * groups * (tile + 2) * 8 + SL_STAGES * 8 + 64;
+    return (size_t)(SL_STAGES + SL_OSTAGES) * groups * stride * 8 + SL_STAGES * 8 + 64;
 }
 
 // State of one moving-average pass held by one lane: FIFO ring (slot written at global step tau is
@@ -122,12 +128,12 @@ struct PassState {
     }
 };
 
-template <int W>
+template <int W, bool BIG>
 __global__ void __launch_bounds__(SL_THREADS)
 smooth_lanes_kernel(const SpecDesc *__restrict__ sd, int n_spec, int iters)
 {
-    constexpr int T = SmoothTile<W>::T;
-    constexpr int STRIDE = T + 2;  // doubles; (T+2)*8 bytes keeps rows 16-byte aligned
+    constexpr int T = SmoothTile<W, BIG>::T;
+    constexpr int STRIDE = SmoothTile<W, BIG>::STRIDE;
     constexpr int R = W / 2;
     static_assert(T % W == 0 && T % 2 == 0, "tile must hold whole ring rotations and 16-byte rows");
 
@@ -324,15 +330,18 @@ smooth_all_passes_kernel(const SmoothAllJob *__restrict__ jobs)
 using SmoothLanesFn = void (*)(const SpecDesc *, int, int);
 
 // Returns the kernel for `window` (2..9) and the tile length, or nullptr when the settings need
-// the generic path (window > 9 or more than 32 iterations).
-inline SmoothLanesFn smooth_lanes_lookup(int window, int iterations, int *tile)
+// the generic path (window > 9, more than 32 iterations, or a pipeline lag longer than a tile).
+inline SmoothLanesFn smooth_lanes_lookup(int window, int iterations, int *stride)
 {
     if (iterations < 1 || iterations > 32) return nullptr;
+    const bool big = iterations >= 3;  // at most 10 spectra per warp
     // the output stream lags the input by L = r + (I-1)(W+r) steps; the two-tile output window needs L <= T
 #define MDB_SL_CASE(Wv) \
     if (window == Wv) { \
-        if ((Wv / 2) + (iterations - 1) * (Wv + Wv / 2) > SmoothTile<Wv>::T) return nullptr; \
-        *tile = SmoothTile<Wv>::T; return smooth_lanes_kernel<Wv>; }
+        const int t = big ? SmoothTile<Wv, true>::T : SmoothTile<Wv, false>::T; \
+        if ((Wv / 2) + (iterations - 1) * (Wv + Wv / 2) > t) return nullptr; \
+        *stride = big ? SmoothTile<Wv, true>::STRIDE : SmoothTile<Wv, false>::STRIDE; \
+        return big ? smooth_lanes_kernel<Wv, true> : smooth_lanes_kernel<Wv, false>; }
     MDB_SL_CASE(2) MDB_SL_CASE(3) MDB_SL_CASE(4) MDB_SL_CASE(5) MDB_SL_CASE(6) MDB_SL_CASE(7) MDB_SL_CASE(8) MDB_SL_CASE(9)
 #undef MDB_SL_CASE
     return nullptr;
