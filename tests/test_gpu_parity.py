@@ -307,6 +307,37 @@ def test_detection_edge_inputs():
     _check_detect(y, "nan")
 
 
+def _signal_from_d2(d2):
+    """Integrate a prescribed second difference twice: y[j+2] = d2[j] - y[j] + 2 y[j+1]."""
+    y = np.zeros(len(d2) + 2)
+    for j, v in enumerate(d2):
+        y[j + 2] = v - y[j] + 2.0 * y[j + 1]
+    return y
+
+
+@pytest.mark.parametrize("centre", [200, 450, 511, 512, 513, 575, 1023, 1024, 1500])
+@pytest.mark.parametrize("run", [3, 70, 200, 700])
+def test_detection_walks_leaving_the_shared_memory_window(centre, run):
+    """Borders further away than the kernel's 64-point halo (and across one or more 512-point
+    tiles) take the global-memory continuation of the walks and of the left score sum; the result
+    must not depend on the tiling.  d2 is prescribed: a long strictly decreasing run into the
+    centre and a long strictly increasing run out of it, placed at and around tile edges."""
+    n = 2600
+    rng = np.random.default_rng(centre * 1000 + run)
+    d2 = rng.integers(-3, 4, n - 2).astype(np.float64)           # small integers: exact arithmetic, many ties
+    c = centre                                                   # centre index in intensity space: minimum at d2[c-1]
+    lo, hi = max(0, c - 1 - run), min(n - 3, c - 1 + run)
+    d2[lo:c - 1] = 1000.0 + np.arange(c - 1 - lo, 0, -1)         # ... 1003, 1002, 1001 (decreasing)
+    d2[c - 1] = -50.0
+    d2[c:hi + 1] = 2000.0 + np.arange(1, hi - c + 2)             # 2001, 2002, ... (increasing)
+    y = _signal_from_d2(d2)
+    assert np.array_equal(O.second_derivative(y), d2)            # integers stay exact
+    pk = _check_detect(y, f"centre={centre} run={run}")
+    if lo > 0 and hi < n - 3:  # both runs end inside the spectrum: the planted peak has its borders at the run ends
+        hit = pk[pk[:, 1] == c]
+        assert hit.shape[0] == 1 and hit[0, 0] == lo + 1 and hit[0, 2] == hi + 1
+
+
 # ------------------------------------------------------------------------------ selection (K4)
 def _check_select(dec, okind, thr, sm, sb_idx, ig, what):
     st, pk, (mean, sd) = gpu_select(dec, sm, sb_idx, ig)
