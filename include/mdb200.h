@@ -107,6 +107,12 @@ uint32_t mdb_abi_version(void);
 const char *mdb_last_error_message(void);
 /* Number of CUDA devices visible; 0 when there is none (compute calls then fail loudly). */
 int mdb_device_count(void);
+/* GPUs used by ONE mdb_deconvolute_spectra call on host-memory batches: 1 (default) = the calling
+ * thread's current device; 0 = every visible device; n = CUDA devices 0..n-1.  With more than one,
+ * the batch is cut into contiguous shards, one host thread and one pipeline per GPU, no exchange
+ * between them (the in-process form of deconvoluter.rs:699-710's rayon-over-spectra).  The
+ * environment variable MDB_DEVICES ("all" or a number) overrides it. */
+mdb_status mdb_set_device_count(int n);
 /* Page-locked host memory for callers that want full-rate H2D (optional helper). */
 mdb_status mdb_host_alloc(void **ptr, size_t bytes);
 mdb_status mdb_host_free(void *ptr);

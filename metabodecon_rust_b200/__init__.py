@@ -12,4 +12,13 @@ from .spectrum import Spectrum
 
 __version__ = "0.1.0"
 
-__all__ = ["__version__", "Deconvoluter", "Deconvolution", "Lorentzian", "Spectrum", "exceptions"]
+
+def set_devices(n: int) -> None:
+    """GPUs used by one `deconvolute_spectra` call: 1 = current device (default), 0 = all visible,
+    n = CUDA devices 0..n-1 (contiguous shards of the batch, one pipeline per GPU, no exchange)."""
+    from . import _lib
+    from .exceptions import raise_for_status
+    raise_for_status(_lib.load().mdb_set_device_count(int(n)), _lib.last_error())
+
+
+__all__ = ["__version__", "set_devices", "Deconvoluter", "Deconvolution", "Lorentzian", "Spectrum", "exceptions"]

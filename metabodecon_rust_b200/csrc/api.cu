@@ -20,6 +20,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -489,9 +490,11 @@ static mdb_status acquire_workspace(Workspace **out)
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
     {
+        // most recently released first: it is the one whose buffers match the current chunk size
         std::lock_guard<std::mutex> lock(g_pool_mutex);
-        auto it = g_pool.find(dev);
-        if (it != g_pool.end()) {
+        auto range = g_pool.equal_range(dev);
+        if (range.first != range.second) {
+            auto it = std::prev(range.second);
             *out = it->second;
             g_pool.erase(it);
             return MDB_OK;
@@ -1147,6 +1150,30 @@ static mdb_status run_pipeline(const mdb_deconvoluter &dc, const std::vector<Hos
     return st;
 }
 
+// ---------------------------------------------------------------------------------------------
+// In-process multi-GPU sharding (host-memory batches only)
+// ---------------------------------------------------------------------------------------------
+static std::atomic<int> g_device_policy{1};  // 1 = the calling thread's current device; 0 = all visible; n = first n
+
+extern "C" mdb_status mdb_set_device_count(int n)
+{
+    if (n < 0) return fail(MDB_ERR_INVALID_ARGUMENT, "mdb_set_device_count: n must be >= 0 (0 = all visible devices)");
+    g_device_policy.store(n);
+    return MDB_OK;
+}
+
+static int devices_to_use(size_t n_spectra)
+{
+    int want = g_device_policy.load();
+    if (const char *env = std::getenv("MDB_DEVICES")) want = std::strcmp(env, "all") == 0 ? 0 : std::atoi(env);
+    if (want == 1) return 1;
+    int visible = 0;
+    if (cudaGetDeviceCount(&visible) != cudaSuccess) { cudaGetLastError(); return 1; }
+    int n = (want <= 0) ? visible : std::min(want, visible);
+    while (n > 1 && n_spectra < (size_t)2 * n) --n;  // at least two spectra per device
+    return std::max(n, 1);
+}
+
 extern "C" size_t mdb_batch_len(const mdb_batch *b) { return b ? b->r.size() : 0; }
 extern "C" mdb_status mdb_batch_status(const mdb_batch *b, size_t i)
 {
@@ -1190,7 +1217,34 @@ extern "C" mdb_status mdb_deconvolute_spectra(const mdb_deconvoluter *d, const m
     std::vector<HostSpec> hs;
     if ((st = build_host_specs(*d, spectra, n_spectra, memory, hs)) != MDB_OK) return st;
 
-    st = run_pipeline(*d, hs, memory, batch->r);
+    const int n_dev = (memory == MDB_MEM_HOST) ? devices_to_use(n_spectra) : 1;
+    if (n_dev <= 1) {
+        st = run_pipeline(*d, hs, memory, batch->r);
+    } else {
+        // One host thread per GPU, contiguous shards, no exchange: the in-process form of the
+        // one-process-per-GPU sharding.  Device d of the shard list is CUDA device d.
+        std::vector<mdb_status> sts(n_dev, MDB_OK);
+        std::vector<std::string> msgs(n_dev);
+        std::vector<std::thread> threads;
+        for (int dev = 0; dev < n_dev; ++dev) {
+            threads.emplace_back([&, dev]() {
+                const size_t lo = (size_t)dev * n_spectra / n_dev, hi = (size_t)(dev + 1) * n_spectra / n_dev;
+                if (cudaSetDevice(dev) != cudaSuccess) {
+                    sts[dev] = MDB_ERR_CUDA;
+                    msgs[dev] = "cudaSetDevice(" + std::to_string(dev) + ") failed";
+                    return;
+                }
+                std::vector<HostSpec> shard(hs.begin() + lo, hs.begin() + hi);
+                std::vector<SpecResult> res(hi - lo);
+                sts[dev] = run_pipeline(*d, shard, memory, res);
+                if (sts[dev] != MDB_OK) msgs[dev] = g_last_error;  // thread-local in the worker
+                for (size_t i = lo; i < hi; ++i) batch->r[i] = std::move(res[i - lo]);
+            });
+        }
+        for (auto &t : threads) t.join();
+        for (int dev = 0; dev < n_dev && st == MDB_OK; ++dev)
+            if (sts[dev] != MDB_OK) st = fail(sts[dev], "device " + std::to_string(dev) + ": " + msgs[dev]);
+    }
     if (st != MDB_OK) return st;
     mdb_status first = MDB_OK;
     for (size_t s = 0; s < n_spectra; ++s)

@@ -617,3 +617,29 @@ def test_optimize_settings_error_leaves_settings_unchanged():
     with pytest.raises(exceptions.NoPeaksDetected):
         dec.optimize_settings(flat)
     assert before == (dec.smoothing_settings(), dec.selection_settings(), dec.fitting_settings())
+
+
+# ------------------------------------------------------------------------------ in-process multi-GPU
+def test_in_process_device_sharding_matches_single_device():
+    """mdb_set_device_count: the batch is cut into contiguous shards, one pipeline per GPU.  On a
+    one-GPU box the request degrades to one device; either way results equal the default path."""
+    import metabodecon_rust_b200 as M
+    n = 8192
+    x = synth.axis(n)
+    specs = [Spectrum(x, synth.config3(300 + s, n=n, x=x), (-2.2, 11.8)) for s in range(9)]
+    dec = Deconvoluter()
+    base = dec.deconvolute_spectra(specs)
+    M.set_devices(0)  # all visible devices
+    try:
+        multi = dec.deconvolute_spectra(specs)
+        bad = specs[:5] + [Spectrum(x, np.zeros(n), (-2.2, 11.8))] + specs[5:]
+        with pytest.raises(exceptions.NoPeaksDetected):
+            dec.deconvolute_spectra(bad)
+    finally:
+        M.set_devices(1)
+    for i, (a, b) in enumerate(zip(base, multi)):
+        assert np.array_equal(a.peaks, b.peaks)
+        assert_bit_equal(a.parameters, b.parameters, f"shard result {i}")
+        assert a.mse == b.mse
+    with pytest.raises(Exception):
+        M.set_devices(-1)
