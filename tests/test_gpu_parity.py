@@ -643,3 +643,71 @@ def test_in_process_device_sharding_matches_single_device():
         assert a.mse == b.mse
     with pytest.raises(Exception):
         M.set_devices(-1)
+
+
+# ------------------------------------------------------------------------------ full-size properties
+# BASELINE.json sizes, where the oracle would take minutes: size-independent exact properties.
+def _config5_batch(n_spec, n=131072):
+    x = synth.axis(n)
+    base = synth.config5(11, n=n, x=x)
+    rng = np.random.default_rng(5)
+    return x, [base + rng.normal(0.0, 40.0, n) for _ in range(n_spec)]
+
+
+def test_full_size_power_of_two_scaling_is_exact():
+    """Multiplying the intensities by 2^k is exact in binary floating point and commutes with every
+    operation of the path (sums, the 1/len products, comparisons, the three-point solve, the
+    division): peaks must be identical, sfhw scale by 2^k, hw2 and maxp stay, the MSE scales by 4^k
+    -- bit for bit, at 2^17 points and ~2,100 peaks per spectrum."""
+    x, ys = _config5_batch(3)
+    dec = Deconvoluter()
+    base = dec.deconvolute_spectra([Spectrum(x, y, (-2.2, 11.8)) for y in ys])
+    for k in (3, -7):
+        f = 2.0 ** k
+        scaled = dec.deconvolute_spectra([Spectrum(x, y * f, (-2.2, 11.8)) for y in ys])
+        for a, b in zip(base, scaled):
+            assert a.peaks.shape[0] > 1500
+            assert np.array_equal(a.peaks, b.peaks)
+            assert_bit_equal(b.parameters[:, 0], a.parameters[:, 0] * f, f"sfhw x 2^{k}")
+            assert_bit_equal(b.parameters[:, 1:], a.parameters[:, 1:], f"hw2, maxp under 2^{k}")
+            assert_bit_equal([b.mse], [a.mse * f * f], f"mse x 4^{k}")
+
+
+def test_full_size_results_do_not_depend_on_batch_position():
+    """The same spectrum placed at different batch indices (different chunks, streams, CTAs and
+    tile offsets; 150 spectra = several adaptive chunks) must give identical bits every time."""
+    x, ys = _config5_batch(2)
+    order = [0, 1] * 75
+    dec = Deconvoluter()
+    outs = dec.deconvolute_spectra([Spectrum(x, ys[i], (-2.2, 11.8)) for i in order])
+    ref = {0: outs[0], 1: outs[1]}
+    for i, out in zip(order, outs):
+        assert np.array_equal(out.peaks, ref[i].peaks)
+        assert_bit_equal(out.parameters, ref[i].parameters, "batch position")
+        assert out.mse == ref[i].mse
+    # and a sample of it agrees with the oracle
+    r = O.deconvolute_spectrum(O.Settings(), x, ys[1], synth.SIGNAL_BOUNDARIES)
+    assert_bit_equal(outs[1].parameters, r.lorentzians, "oracle spot check")
+
+
+def test_config4_size_superposition_grid_split_and_scaling():
+    """Config 4 scale (2^24 grid points x 20,000 Lorentzians would take the oracle ~10 minutes; a
+    2^22-point slice of it is used here): grid points are independent, so evaluating the grid in
+    slices (the multi-GPU sharding) must reproduce the one-shot result bit for bit, scaling sfhw by
+    a power of two scales every value exactly, and 4,096 sampled points agree with the oracle."""
+    from metabodecon_rust_b200.lorentzian import superposition_vec_array
+    rng = np.random.Generator(np.random.PCG64(20260004))
+    p = 20000
+    maxp = rng.uniform(0.0, 10.0, p)
+    hw = np.exp(rng.uniform(np.log(5e-4), np.log(3e-3), p))
+    sf = np.exp(rng.uniform(0.0, np.log(1e4), p))
+    lor = np.ascontiguousarray(np.stack([sf * hw, hw * hw, maxp], axis=1))
+    x = np.linspace(-2.2, 11.8, 1 << 24)[: 1 << 22]
+    whole = superposition_vec_array(x, lor)
+    parts = np.concatenate([superposition_vec_array(x[lo:hi], lor) for lo, hi in ((0, 1000001), (1000001, 3 << 20), (3 << 20, 1 << 22))])
+    assert_bit_equal(parts, whole, "grid slices")
+    lor8 = lor.copy()
+    lor8[:, 0] *= 8.0
+    assert_bit_equal(superposition_vec_array(x, lor8), whole * 8.0, "sfhw x 8")
+    idx = rng.integers(0, x.size, 4096)
+    assert_bit_equal(whole[idx], O.superposition_vec(x[idx], lor, parallel=True), "oracle sample")
