@@ -711,3 +711,24 @@ def test_config4_size_superposition_grid_split_and_scaling():
     assert_bit_equal(superposition_vec_array(x, lor8), whole * 8.0, "sfhw x 8")
     idx = rng.integers(0, x.size, 4096)
     assert_bit_equal(whole[idx], O.superposition_vec(x[idx], lor, parallel=True), "oracle sample")
+
+
+# ------------------------------------------------------------------------------ the ABI from plain C
+def test_c_host_program_through_the_abi(golden_dir, tmp_path):
+    """examples/deconvolute.c: a compiled host linking libmdb200.so directly (no Python, no torch
+    types) reproduces BASELINE config 1 -- the Appendix-B checkpoints, bit for bit."""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    gcc = shutil.which("gcc") or "/usr/bin/gcc"
+    exe = str(tmp_path / "deconvolute")
+    libdir = os.path.join(root, "metabodecon_rust_b200")
+    subprocess.run([gcc, "-O2", "-I" + os.path.join(root, "include"), os.path.join(root, "examples", "deconvolute.c"),
+                    "-o", exe, "-L" + libdir, "-lmdb200", "-Wl,-rpath," + libdir, "-lm"], check=True)
+    out = subprocess.run([exe, os.path.join(golden_dir, "bruker", "blood_01", "10", "pdata", "10", "1r")],
+                         check=True, capture_output=True, text=True).stdout
+    first = out.splitlines()[0].split()
+    assert first[:6] == ["points", "131072", "selected_peaks", "981", "lorentzians", "760"]
+    assert float.fromhex(first[7]) == float.fromhex("0x1.0808a64fe177ep+35")      # SURVEY.md Appendix B
+    l0 = out.splitlines()[1].split()
+    assert float.fromhex(l0[2]) == float.fromhex("0x1.084fd4b50b8dfp-4") and float.fromhex(l0[6]) == float.fromhex("0x1.0eac0d0cd9679p+3")
