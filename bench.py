@@ -165,6 +165,8 @@ def main():
     ap.add_argument("--sup-lorentzians", type=int, default=20000, help="config 4: Lorentzians")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--host-memory", default="pinned", choices=["pinned", "pageable"],
+                    help="host buffers of the e2e measurement (pageable = what NumPy callers hand over)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -288,16 +290,19 @@ def main():
     # ---- e2e: host (pinned) buffers through the C ABI, copies inside the timed region
     e2e = None
     if not args.no_e2e:
-        y_host = torch.empty((S, N_POINTS), dtype=torch.float64, pin_memory=True)
+        pin = args.host_memory == "pinned"
+        y_host = torch.empty((S, N_POINTS), dtype=torch.float64, pin_memory=pin)
         y_host.copy_(y_dev)
-        x_host = torch.from_numpy(x_np.copy()).pin_memory()
+        x_host = torch.from_numpy(x_np.copy())
+        if pin:
+            x_host = x_host.pin_memory()
         torch.cuda.synchronize()
         host_views = make_views(x_host.data_ptr(), y_host.data_ptr())
         ms_host, _ = timed(host_views, _lib.MDB_MEM_HOST, max(1, args.warmup), args.steps)
         # bytes as counted by the library around its own copies (mdb_transfer_bytes): intensities, the
         # axis once per chunk and descriptors going in; counts, peaks, Lorentzians and MSEs coming out
         e2e = {"value": world * S / (ms_host / 1e3), "unit": "spectra/s", "h2d_bytes_per_step": int(stats["h2d_per_step"]),
-               "d2h_bytes_per_step": int(stats["d2h_per_step"]), "ms_per_step": ms_host, "host_memory": "pinned"}
+               "d2h_bytes_per_step": int(stats["d2h_per_step"]), "ms_per_step": ms_host, "host_memory": args.host_memory}
 
     # ---- config 4: one superposition_vec over a 2^24-point grid x 20,000 Lorentzians, the grid
     # sharded contiguously over the ranks (strong scaling), parameters replicated, no exchange

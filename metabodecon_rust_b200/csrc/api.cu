@@ -461,7 +461,7 @@ struct Workspace {
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     // stage A
     DevBuf x, y, ys, tmp, tile_cnt, pk, sc, sfr, sel, ig, desc, sel_out;
-    PinBuf h_desc, h_ig, h_sel_out;
+    PinBuf h_desc, h_ig, h_sel_out, h_stage;
     // stage B
     DevBuf fdesc, segs, fit_state, par_a, par_b, lor, n_kept, resid, mse, peaks_dense;
     PinBuf h_fdesc, h_segs, h_lor, h_n_kept, h_mse, h_peaks;
@@ -470,7 +470,7 @@ struct Workspace {
         for (DevBuf *b : {&x, &y, &ys, &tmp, &tile_cnt, &pk, &sc, &sfr, &sel, &ig, &desc, &sel_out, &fdesc,
                           &segs, &fit_state, &par_a, &par_b, &lor, &n_kept, &resid, &mse, &peaks_dense})
             b->release();
-        for (PinBuf *b : {&h_desc, &h_ig, &h_sel_out, &h_fdesc, &h_segs, &h_lor, &h_n_kept, &h_mse, &h_peaks})
+        for (PinBuf *b : {&h_desc, &h_ig, &h_sel_out, &h_stage, &h_fdesc, &h_segs, &h_lor, &h_n_kept, &h_mse, &h_peaks})
             b->release();
         if (ev_a) cudaEventDestroy(ev_a);
         if (ev_b) cudaEventDestroy(ev_b);
@@ -684,6 +684,18 @@ static mdb_status launch_smooth(cudaStream_t stream, const SpecDesc *d_desc, con
     return MDB_OK;
 }
 
+// True when the intensity rows of the chunk live in page-locked (or managed) host memory.  Rows
+// are probed individually (a batch may mix allocations); the probe costs about a microsecond.
+static bool host_rows_pinned(const std::vector<HostSpec> &hs, size_t first, size_t count)
+{
+    for (size_t s = 0; s < count; ++s) {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, hs[first + s].y) != cudaSuccess) { cudaGetLastError(); return false; }
+        if (attr.type == cudaMemoryTypeUnregistered) return false;
+    }
+    return true;
+}
+
 // Stage A: inputs -> device, smoothing, detection, selection, counts back to the host.
 static mdb_status stage_a(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_deconvoluter &dc, int memory,
                           bool skip_smoothing_input_is_smoothed)
@@ -778,18 +790,38 @@ static mdb_status stage_a(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
                 if (hs[ck.first + s].x == kv.first) { n = hs[ck.first + s].n; break; }
             CUDA_TRY(counted_memcpy_async(ws.x.as<double>() + kv.second, kv.first, n * 8, cudaMemcpyHostToDevice, ws.stream));
         }
-        size_t s = 0;
-        while (s < S) {
-            size_t e = s + 1;
-            const HostSpec &h0 = hs[ck.first + s];
-            size_t bytes = h0.n * 8;
-            while (e < S) {
-                const HostSpec &hp = hs[ck.first + e - 1], &hn = hs[ck.first + e];
-                if (hp.n % 16 == 0 && hn.y == hp.y + hp.n) { bytes += hn.n * 8; ++e; }
-                else break;
+        if (!host_rows_pinned(hs, ck.first, S)) {
+            // Pageable rows (what NumPy / Vec<f64> callers hand over): the driver would stage them
+            // through its own bounce buffer on this thread at ~10 GB/s.  Gather them instead into
+            // the workspace's pinned staging area with a few host threads (laid out exactly like
+            // ws.y), then one full-rate DMA.
+            CUDA_TRY(ws.h_stage.ensure(y_elems * 8));
+            double *stage = ws.h_stage.as<double>();
+            CUDA_TRY(cudaStreamSynchronize(ws.stream));  // the previous DMA out of this staging area has finished
+            const unsigned hw = std::max(2u, std::thread::hardware_concurrency());
+            const size_t n_thr = std::min<size_t>({(size_t)8, (size_t)hw / 2, S});
+            std::vector<std::thread> pool;
+            for (size_t t = 0; t < n_thr; ++t)
+                pool.emplace_back([&, t]() {
+                    for (size_t s = t; s < S; s += n_thr)
+                        std::memcpy(stage + y_off[s], hs[ck.first + s].y, hs[ck.first + s].n * 8);
+                });
+            for (auto &th : pool) th.join();
+            CUDA_TRY(counted_memcpy_async(y_dst, stage, y_elems * 8, cudaMemcpyHostToDevice, ws.stream));
+        } else {
+            size_t s = 0;
+            while (s < S) {
+                size_t e = s + 1;
+                const HostSpec &h0 = hs[ck.first + s];
+                size_t bytes = h0.n * 8;
+                while (e < S) {
+                    const HostSpec &hp = hs[ck.first + e - 1], &hn = hs[ck.first + e];
+                    if (hp.n % 16 == 0 && hn.y == hp.y + hp.n) { bytes += hn.n * 8; ++e; }
+                    else break;
+                }
+                CUDA_TRY(counted_memcpy_async(y_dst + y_off[s], h0.y, bytes, cudaMemcpyHostToDevice, ws.stream));
+                s = e;
             }
-            CUDA_TRY(counted_memcpy_async(y_dst + y_off[s], h0.y, bytes, cudaMemcpyHostToDevice, ws.stream));
-            s = e;
         }
     } else if (skip_smoothing_input_is_smoothed) {
         for (size_t s = 0; s < S; ++s)
