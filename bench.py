@@ -375,7 +375,8 @@ def main():
         pipe_rate = N_SM * FP64_LANES_PER_SM * sm_mhz * 1e6
         return {"bound": "fp64", "kernel": name, "achieved": achieved, "peak": fp64_peak_tflops, "unit": "TFLOP/s",
                 "frac": achieved / fp64_peak_tflops, "traffic": traffic(name),
-                "peak_source": f"computed: {N_SM} SMs x {FP64_LANES_PER_SM} FP64 lanes x 2 x {sm_max:.0f} MHz (not in MEASURED_PEAKS.json)",
+                "peak_source": f"computed: {N_SM} SMs x {FP64_LANES_PER_SM} FP64 lanes x 2 x {sm_max:.0f} MHz (MEASURED_PEAKS.json has no FP64 entry; "
+                               "tools/kbench.cu measures 98.5-99 % of the corresponding instruction rate with DADD/DMUL/DFMA streams, profiles/kbench_r1.txt)",
                 "evals_per_s": evals_per_s, "evals_per_launch": p["work"] / p["launches"],
                 "ms_per_launch": p["ms"] / p["launches"], "launches": p["launches"],
                 "fp64_pipe_util": evals_per_s * FP64_INSTR_PER_EVAL / pipe_rate,
