@@ -161,6 +161,8 @@ def main():
     ap.add_argument("--spectra", type=int, default=2000, help="spectra per GPU per step")
     ap.add_argument("--cpu-sample", type=int, default=0, help="spectra in the CPU baseline sample (0 = 16 x cores)")
     ap.add_argument("--no-superposition", action="store_true", help="skip the config-4 superposition_vec measurement")
+    ap.add_argument("--no-smooth-saturation", action="store_true",
+                    help="skip the K1 launch-size sweep (smoothing GB/s at 64 ... 5920 spectra per launch)")
     ap.add_argument("--sup-points", type=int, default=1 << 24, help="config 4: grid points (whole job, sharded over the GPUs)")
     ap.add_argument("--sup-lorentzians", type=int, default=20000, help="config 4: Lorentzians")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -340,6 +342,27 @@ def main():
                "checksum": float(out4[:: max(1, (hi - lo) // 1024)].sum().item())}
         del x4, out4
 
+    # ---- K1 alone at growing launch sizes: the exact-recurrence smoothing runs at chain latency, so
+    # its GB/s is set by how many spectra share a launch; it turns bandwidth bound only with
+    # thousands of them.  Reuses the batch as input, rank 0 at N = 1 only.
+    smooth_sat = None
+    if not args.no_smooth_saturation and world == 1:
+        smooth_sat = []
+        for count in (64, 512, 1480, 2960, 5920, 11840):
+            reps = (count + S - 1) // S
+            src = y_dev if reps == 1 else y_dev.repeat(reps, 1)
+            src = src[:count].contiguous()
+            dst = torch.empty_like(src)
+            ms_k = C.c_double()
+            best = None
+            for _ in range(3):
+                st = lib.mdb_stage_smooth_batch(src.data_ptr(), N_POINTS, count, N_POINTS, 3, 3, dst.data_ptr(), C.byref(ms_k))
+                assert st == 0, _lib.last_error()
+                best = ms_k.value if best is None else min(best, ms_k.value)
+            smooth_sat.append({"spectra_per_launch": count, "ms": best, "gb_per_s": 16.0 * N_POINTS * count / (best / 1e3) / 1e9})
+            del src, dst
+        torch.cuda.empty_cache()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -445,6 +468,8 @@ def main():
         "kernel_ms_serial_step": {k: v["ms"] for k, v in prof.items() if v["launches"]},
         "serial_step_ms": ms_serial, "roofline_pass": f"one extra step, chunks of {ROOFLINE_CHUNK} spectra, one chunk at a time",
         "superposition_vec": sup,
+        "smooth_launch_size_sweep": None if smooth_sat is None else
+        [dict(e, frac_of_hbm_peak=e["gb_per_s"] / hbm_peak) for e in smooth_sat],
         "cpu_baseline": cpu, "parity_sample": parity,
     }
     print(json.dumps(line), flush=True)

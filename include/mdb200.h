@@ -245,6 +245,11 @@ mdb_status mdb_superposition_vec(const double *x, size_t n, const mdb_lorentzian
 /* MovingAverage::smooth_values  smoothing/moving_average.rs:53-83 (out may alias values). */
 mdb_status mdb_stage_smooth(const double *values, size_t n, uint64_t iterations,
                             uint64_t window_size, double *out);
+/* K1 on `count` equally long spectra already in DEVICE memory (rows of `stride` doubles), one
+ * launch; *ms (optional) = kernel time from CUDA events.  Measurement aid: shows the launch size at
+ * which the exact-recurrence smoothing turns from latency bound to bandwidth bound. */
+mdb_status mdb_stage_smooth_batch(const double *values_dev, size_t n, size_t count, size_t stride,
+                                  uint64_t iterations, uint64_t window_size, double *out_dev, double *ms);
 /* second_derivative + Detector::detect_peaks  peak_selection/common.rs:5-10, detector.rs:99-113,
  * plus ScorerMinimumSum::score_peak (scorer.rs:65-74) for every detected triplet.
  * peaks: 3*cap int32 (left, center, right); scores: cap doubles; *n_found may exceed cap. */

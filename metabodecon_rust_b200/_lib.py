@@ -105,6 +105,7 @@ SIGNATURES = [
     ("mdb_deconvoluter_optimize_settings", C.c_int, [_P, C.POINTER(SpectrumView), C.c_int, _DP]),
     ("mdb_superposition_vec", C.c_int, [_P, C.c_size_t, _P, C.c_size_t, _P, C.c_int]),
     ("mdb_stage_smooth", C.c_int, [_P, C.c_size_t, C.c_uint64, C.c_uint64, _P]),
+    ("mdb_stage_smooth_batch", C.c_int, [_P, C.c_size_t, C.c_size_t, C.c_size_t, C.c_uint64, C.c_uint64, _P, _DP]),
     ("mdb_stage_detect", C.c_int, [_P, C.c_size_t, _P, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
     ("mdb_stage_select", C.c_int, [_P, _P, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, _P, C.c_size_t,
                                   _P, C.c_size_t, C.POINTER(C.c_size_t), _DP]),

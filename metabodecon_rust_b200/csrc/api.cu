@@ -664,13 +664,13 @@ static mdb_status launch_smooth(cudaStream_t stream, const SpecDesc *d_desc, con
         pts += (double)d.n;
         aligned = aligned && (((uintptr_t)d.y & 15) == 0) && (((uintptr_t)d.ys & 15) == 0);
     }
-    int stride = 0;
-    SmoothLanesFn fn = smooth_lanes_lookup(window, iters, &stride);
+    int stride = 0, in_stages = 0;
+    SmoothLanesFn fn = smooth_lanes_lookup(window, iters, S, sm_count(), &stride, &in_stages);
     const char *force = std::getenv("MDB_SMOOTH_GENERIC");
     prof_begin(spans, MDB_KERNEL_SMOOTH, stream);
     if (fn && aligned && !(force && force[0] == '1')) {
         const int groups = 32 / iters;  // spectra per warp: one lane per (spectrum, pass)
-        const size_t smem = smooth_lanes_smem_bytes(stride, groups);
+        const size_t smem = smooth_lanes_smem_bytes(stride, in_stages, groups);
         CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         fn<<<(unsigned)((S + groups - 1) / groups), SL_THREADS, smem, stream>>>(d_desc, (int)S, iters);
         LAUNCH_CHECK();
@@ -1462,6 +1462,52 @@ extern "C" mdb_status mdb_stage_smooth(const double *values, size_t n, uint64_t 
     CUDA_TRY(counted_memcpy_async(out, ws->ys.p, n * 8, cudaMemcpyDeviceToHost, ws->stream));
     CUDA_TRY(cudaStreamSynchronize(ws->stream));
     return MDB_OK;
+}
+
+// Test / measurement entry: K1 on `count` equally long spectra ALREADY IN DEVICE MEMORY (rows of
+// `stride` doubles, 16-byte aligned), one launch.  Lets bench.py show where the exact-recurrence
+// smoothing stops being latency bound (thousands of spectra per launch).  *ms (optional) receives
+// the kernel time measured with CUDA events on the launching stream.
+extern "C" mdb_status mdb_stage_smooth_batch(const double *values_dev, size_t n, size_t count, size_t stride,
+                                             uint64_t iterations, uint64_t window, double *out_dev, double *ms)
+{
+    if (!values_dev || !out_dev || count == 0) return fail(MDB_ERR_INVALID_ARGUMENT, "null argument");
+    if (n < 5 || n >= ((size_t)1 << 31) || stride < n) return fail(MDB_ERR_INVALID_ARGUMENT, "bad length / stride");
+    mdb_smoothing_settings sm = {MDB_SMOOTHING_MOVING_AVERAGE, iterations, window};
+    mdb_status st = validate_smoothing(sm);
+    if (st != MDB_OK) return st;
+    if ((st = require_device()) != MDB_OK) return st;
+    Workspace *ws = nullptr;
+    if ((st = acquire_workspace(&ws)) != MDB_OK) return st;
+    struct Guard { Workspace *w; ~Guard() { cudaStreamSynchronize(w->stream); release_workspace(w); } } guard{ws};
+    std::vector<SpecDesc> descs(count);
+    for (size_t s = 0; s < count; ++s) {
+        descs[s] = SpecDesc{};
+        descs[s].y = values_dev + s * stride;
+        descs[s].ys = out_dev + s * stride;
+        descs[s].n = (int)n;
+    }
+    CUDA_TRY(ws->desc.ensure(count * sizeof(SpecDesc)));
+    if (iterations >= 2) {  // the generic fallback ping-pongs through tmp
+        CUDA_TRY(ws->tmp.ensure(count * stride * 8));
+        for (size_t s = 0; s < count; ++s) descs[s].tmp = ws->tmp.as<double>() + s * stride;
+    }
+    CUDA_TRY(counted_memcpy_async(ws->desc.p, descs.data(), count * sizeof(SpecDesc), cudaMemcpyHostToDevice, ws->stream));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    CUDA_TRY(cudaEventRecord(e0, ws->stream));
+    st = launch_smooth(ws->stream, ws->desc.as<SpecDesc>(), descs, (int)iterations, (int)window, nullptr);
+    if (st == MDB_OK) {
+        CUDA_TRY(cudaEventRecord(e1, ws->stream));
+        CUDA_TRY(cudaStreamSynchronize(ws->stream));
+        float t = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&t, e0, e1));
+        if (ms) *ms = (double)t;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return st;
 }
 
 // Runs stage A on one already-smoothed spectrum held on the host.

@@ -45,25 +45,28 @@ __device__ __forceinline__ void tma_bulk_commit() { asm volatile("cp.async.bulk.
 template <int N> __device__ __forceinline__ void tma_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-constexpr int SL_STAGES = 4;    // input tiles in flight per warp
-constexpr int SL_OSTAGES = 3;   // output tiles in the ring
+constexpr int SL_OSTAGES = 3;   // output tiles in the ring (two being written, one being stored)
 constexpr int SL_THREADS = 32;  // one warp per CTA
 
-// Tile length: a multiple of W (static ring slots) and even (16-byte bulk copies).  BIG tiles
-// (about 224 points) amortise the per-tile costs (mbarrier wait, one bulk copy per row each way,
-// proxy fence) when a warp holds at most 10 spectra (3 or more passes); the small tile (about
-// 112) keeps the 32-spectra case (1 pass) inside the shared-memory limit.
-template <int W, bool BIG> struct SmoothTile {
-    static constexpr int Q = (BIG ? 224 : 112) / W;
+// Tile length: a multiple of W (static ring slots) and even (16-byte bulk copies).  Three classes:
+//   CLS 0  ~224 points, 4 input stages: amortises the per-tile costs (mbarrier wait, one bulk copy
+//          per row each way, proxy fence) when a warp holds <= 10 spectra and the launch has at most
+//          one warp per SM (its ~126 KB of shared memory allow no more);
+//   CLS 1  ~112 points, 4 input stages: the 32-spectra-per-warp case (1 pass) and mid-size launches;
+//   CLS 2  ~56 points, 3 input stages (~28 KB per warp): launches with thousands of spectra, where
+//          eight warps per SM turn the kernel from latency bound to bandwidth bound.
+template <int W, int CLS> struct SmoothTile {
+    static constexpr int Q = (CLS == 0 ? 224 : CLS == 1 ? 112 : 56) / W;
     static constexpr int T = W * ((W % 2) ? (Q & ~1) : Q);
+    static constexpr int IN_STAGES = CLS == 2 ? 3 : 4;  // input tiles in flight per warp
     // row stride in doubles: even (16-byte rows for the bulk copies) with an odd half, so that the
     // rows of the spectra sharing a warp start in different shared-memory banks
     static constexpr int STRIDE = ((T + 2) / 2) % 2 ? T + 2 : T + 4;
 };
 
-inline size_t smooth_lanes_smem_bytes(int stride, int groups)
+inline size_t smooth_lanes_smem_bytes(int stride, int in_stages, int groups)
 {
-    return (size_t)(SL_STAGES + SL_OSTAGES) * groups * stride * 8 + SL_STAGES * 8 + 64;
+    return (size_t)(in_stages + SL_OSTAGES) * groups * stride * 8 + in_stages * 8 + 64;
 }
 
 // State of one moving-average pass held by one lane: FIFO ring (slot written at global step tau is
@@ -128,12 +131,13 @@ struct PassState {
     }
 };
 
-template <int W, bool BIG>
+template <int W, int CLS>
 __global__ void __launch_bounds__(SL_THREADS)
 smooth_lanes_kernel(const SpecDesc *__restrict__ sd, int n_spec, int iters)
 {
-    constexpr int T = SmoothTile<W, BIG>::T;
-    constexpr int STRIDE = SmoothTile<W, BIG>::STRIDE;
+    constexpr int T = SmoothTile<W, CLS>::T;
+    constexpr int STRIDE = SmoothTile<W, CLS>::STRIDE;
+    constexpr int SL_STAGES = SmoothTile<W, CLS>::IN_STAGES;
     constexpr int R = W / 2;
     static_assert(T % W == 0 && T % 2 == 0, "tile must hold whole ring rotations and 16-byte rows");
 
@@ -331,17 +335,22 @@ using SmoothLanesFn = void (*)(const SpecDesc *, int, int);
 
 // Returns the kernel for `window` (2..9) and the tile length, or nullptr when the settings need
 // the generic path (window > 9, more than 32 iterations, or a pipeline lag longer than a tile).
-inline SmoothLanesFn smooth_lanes_lookup(int window, int iterations, int *stride)
+inline SmoothLanesFn smooth_lanes_lookup(int window, int iterations, size_t n_spectra, int sm_count, int *stride,
+                                         int *in_stages)
 {
     if (iterations < 1 || iterations > 32) return nullptr;
-    const bool big = iterations >= 3;  // at most 10 spectra per warp
-    // the output stream lags the input by L = r + (I-1)(W+r) steps; the two-tile output window needs L <= T
+    const size_t warps = (n_spectra + (size_t)(32 / iterations) - 1) / (size_t)(32 / iterations);
+    const int lag = (window / 2) + (iterations - 1) * (window + window / 2);  // L = r + (I-1)(W+r) must fit a tile
+    int cls = (iterations >= 3 && warps <= (size_t)sm_count) ? 0 : (iterations >= 3 && warps > (size_t)3 * sm_count) ? 2 : 1;
 #define MDB_SL_CASE(Wv) \
     if (window == Wv) { \
-        const int t = big ? SmoothTile<Wv, true>::T : SmoothTile<Wv, false>::T; \
-        if ((Wv / 2) + (iterations - 1) * (Wv + Wv / 2) > t) return nullptr; \
-        *stride = big ? SmoothTile<Wv, true>::STRIDE : SmoothTile<Wv, false>::STRIDE; \
-        return big ? smooth_lanes_kernel<Wv, true> : smooth_lanes_kernel<Wv, false>; }
+        if (cls == 2 && lag > SmoothTile<Wv, 2>::T) cls = 1; \
+        if (cls == 1 && lag > SmoothTile<Wv, 1>::T) cls = iterations >= 3 ? 0 : -1; \
+        if (cls == 0 && lag > SmoothTile<Wv, 0>::T) cls = -1; \
+        if (cls < 0) return nullptr; \
+        *stride = cls == 0 ? SmoothTile<Wv, 0>::STRIDE : cls == 1 ? SmoothTile<Wv, 1>::STRIDE : SmoothTile<Wv, 2>::STRIDE; \
+        *in_stages = cls == 2 ? SmoothTile<Wv, 2>::IN_STAGES : SmoothTile<Wv, 0>::IN_STAGES; \
+        return cls == 0 ? smooth_lanes_kernel<Wv, 0> : cls == 1 ? smooth_lanes_kernel<Wv, 1> : smooth_lanes_kernel<Wv, 2>; }
     MDB_SL_CASE(2) MDB_SL_CASE(3) MDB_SL_CASE(4) MDB_SL_CASE(5) MDB_SL_CASE(6) MDB_SL_CASE(7) MDB_SL_CASE(8) MDB_SL_CASE(9)
 #undef MDB_SL_CASE
     return nullptr;

@@ -158,6 +158,16 @@ extern "C" {
     ) -> mdb_status;
 
     pub fn mdb_stage_smooth(values: *const f64, n: usize, iterations: u64, window_size: u64, out: *mut f64) -> mdb_status;
+    pub fn mdb_stage_smooth_batch(
+        values_dev: *const f64,
+        n: usize,
+        count: usize,
+        stride: usize,
+        iterations: u64,
+        window_size: u64,
+        out_dev: *mut f64,
+        ms: *mut f64,
+    ) -> mdb_status;
     pub fn mdb_stage_detect(
         smoothed: *const f64,
         n: usize,

@@ -256,6 +256,27 @@ def test_smoothing_short_inputs(n):
         assert_bit_equal(gpu_smooth(y, it, w), O.smooth_values(y, it, w), f"n={n} ({it},{w})")
 
 
+def test_smoothing_batch_entry_small_and_large_tile_variants(blood_arrays):
+    """mdb_stage_smooth_batch (device memory, one launch): launches of more warps than SMs take the
+    small-tile kernel, smaller ones the 224-point tile; both must reproduce the oracle."""
+    torch = pytest.importorskip("torch")
+    lib = _lib.load()
+    _, y = blood_arrays
+    n = 20000
+    rows = np.stack([np.roll(y, 997 * s)[:n] for s in range(7)])
+    want = np.stack([O.smooth_values(r, 3, 3) for r in rows])
+    for count in (7, 2000, 4500):  # 1 warp (224-point tiles), 200 warps (112), 450 warps (56)
+        src = torch.from_numpy(rows).cuda().repeat((count + 6) // 7, 1)[:count].contiguous()
+        dst = torch.zeros_like(src)
+        ms = C.c_double()
+        st = lib.mdb_stage_smooth_batch(src.data_ptr(), n, count, n, 3, 3, dst.data_ptr(), C.byref(ms))
+        assert st == 0, _lib.last_error()
+        got = dst.cpu().numpy()
+        for s in range(count):
+            assert_bit_equal(got[s], want[s % 7], f"batch smoothing count={count} row {s}")
+        assert ms.value > 0.0
+
+
 # ------------------------------------------------------------------------------ detection (K2/K3)
 def _check_detect(sm, what):
     pk, sc = gpu_detect(sm)
