@@ -596,6 +596,29 @@ def test_device_resident_inputs_match_host_inputs():
         lib.mdb_batch_free(batch)
 
 
+def test_persistent_fit_kernel_matches_multi_launch(monkeypatch, golden_dir):
+    """MDB_FIT_PERSISTENT=1: all refinement passes in one work-queue launch (an experiment kept
+    behind an environment variable); results must be the same bits, including per-spectrum
+    iteration counts (optimize_settings) and spectra of different peak counts in one chunk."""
+    n = 16384
+    x = synth.axis(n)
+    specs = [Spectrum(x, synth.config3(500 + s, n=n, x=x), (-2.2, 11.8)) for s in range(6)]
+    specs.append(Spectrum(synth.axis(4096), synth.config3(9, n=4096), (-2.2, 11.8)))
+    dec = Deconvoluter()
+    base = dec.deconvolute_spectra(specs)
+    monkeypatch.setenv("MDB_FIT_PERSISTENT", "1")
+    pers = dec.deconvolute_spectra(specs)
+    for a, b in zip(base, pers):
+        assert_bit_equal(b.parameters, a.parameters, "persistent fit")
+        assert a.mse == b.mse
+    sim = Spectrum.read_bruker(os.path.join(golden_dir, "bruker", "sim_01"), 10, 10, (3.339, 3.553))
+    d1, d2 = Deconvoluter(), Deconvoluter()
+    m2 = d2.optimize_settings(sim)
+    monkeypatch.delenv("MDB_FIT_PERSISTENT")
+    m1 = d1.optimize_settings(sim)
+    assert m1 == m2 and d1.fitting_settings() == d2.fitting_settings() and d1.smoothing_settings() == d2.smoothing_settings()
+
+
 # ------------------------------------------------------------------------------ optimize_settings
 def test_optimize_settings_sim_matches_oracle(golden_dir):
     """deconvoluter.rs:761-825 on the reference's own example spectrum (sim_01, 3.339..3.553):
