@@ -799,14 +799,20 @@ static mdb_status stage_a(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
             double *stage = ws.h_stage.as<double>();
             CUDA_TRY(cudaStreamSynchronize(ws.stream));  // the previous DMA out of this staging area has finished
             const unsigned hw = std::max(2u, std::thread::hardware_concurrency());
-            const size_t n_thr = std::min<size_t>({(size_t)8, (size_t)hw / 2, S});
-            std::vector<std::thread> pool;
-            for (size_t t = 0; t < n_thr; ++t)
-                pool.emplace_back([&, t]() {
-                    for (size_t s = t; s < S; s += n_thr)
-                        std::memcpy(stage + y_off[s], hs[ck.first + s].y, hs[ck.first + s].n * 8);
-                });
-            for (auto &th : pool) th.join();
+            size_t n_thr = std::min<size_t>({(size_t)8, (size_t)hw / 2, S});
+            if (y_elems * 8 < ((size_t)4 << 20)) n_thr = 1;  // small chunks: spawning threads costs more than the copy
+            if (n_thr <= 1) {
+                for (size_t s = 0; s < S; ++s)
+                    std::memcpy(stage + y_off[s], hs[ck.first + s].y, hs[ck.first + s].n * 8);
+            } else {
+                std::vector<std::thread> pool;
+                for (size_t t = 0; t < n_thr; ++t)
+                    pool.emplace_back([&, t]() {
+                        for (size_t s = t; s < S; s += n_thr)
+                            std::memcpy(stage + y_off[s], hs[ck.first + s].y, hs[ck.first + s].n * 8);
+                    });
+                for (auto &th : pool) th.join();
+            }
             CUDA_TRY(counted_memcpy_async(y_dst, stage, y_elems * 8, cudaMemcpyHostToDevice, ws.stream));
         } else {
             size_t s = 0;
