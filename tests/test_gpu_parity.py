@@ -457,7 +457,7 @@ def test_fit_bit_exact_synthetic(iterations):
 
 
 def test_fit_many_peaks_tiles():
-    # more peaks than one shared-memory tile (FIT_TILE = 512) and a ragged last block
+    # more peaks than one shared-memory tile (LOR_TILE = 512) and a ragged last block
     n = 131072
     x = synth.axis(n)
     y = synth.config5(0, n=n)
