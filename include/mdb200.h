@@ -200,6 +200,12 @@ size_t mdb_batch_n_peaks(const mdb_batch *b, size_t i);
 /* Selected peaks as (left, center, right) int32 triples, ascending by centre. */
 const int32_t *mdb_batch_peaks(const mdb_batch *b, size_t i);
 void mdb_batch_free(mdb_batch *b);
+/* Bulk accessors for bindings with per-call overhead: totals over the batch, then one export of
+ * every per-spectrum field (any output pointer may be NULL).  status/n_lorentzians/n_peaks/mse hold
+ * mdb_batch_len entries; lorentzians / peaks are the per-spectrum arrays concatenated in order. */
+void mdb_batch_totals(const mdb_batch *b, size_t *n_lorentzians, size_t *n_peaks);
+mdb_status mdb_batch_export(const mdb_batch *b, int32_t *status, uint64_t *n_lorentzians, uint64_t *n_peaks,
+                            double *mse, mdb_lorentzian *lorentzians, int32_t *peaks);
 
 /*
  * Deconvoluter::deconvolute_spectra / par_deconvolute_spectra  (deconvoluter.rs:651-661,

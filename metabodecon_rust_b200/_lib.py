@@ -101,6 +101,8 @@ SIGNATURES = [
     ("mdb_batch_n_peaks", C.c_size_t, [_P, C.c_size_t]),
     ("mdb_batch_peaks", C.POINTER(C.c_int32), [_P, C.c_size_t]),
     ("mdb_batch_free", None, [_P]),
+    ("mdb_batch_totals", None, [_P, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
+    ("mdb_batch_export", C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
     ("mdb_deconvolute_spectra", C.c_int, [_P, C.POINTER(SpectrumView), C.c_size_t, C.c_int, C.POINTER(_P)]),
     ("mdb_deconvoluter_optimize_settings", C.c_int, [_P, C.POINTER(SpectrumView), C.c_int, _DP]),
     ("mdb_superposition_vec", C.c_int, [_P, C.c_size_t, _P, C.c_size_t, _P, C.c_int]),

@@ -1270,6 +1270,35 @@ extern "C" const int32_t *mdb_batch_peaks(const mdb_batch *b, size_t i)
 }
 extern "C" void mdb_batch_free(mdb_batch *b) { delete b; }
 
+// Bulk accessors: one call instead of five per spectrum (language bindings with per-call overhead).
+extern "C" void mdb_batch_totals(const mdb_batch *b, size_t *n_lorentzians, size_t *n_peaks)
+{
+    size_t nl = 0, np = 0;
+    if (b)
+        for (const SpecResult &r : b->r) { nl += r.lor.size(); np += r.peaks.size() / 3; }
+    if (n_lorentzians) *n_lorentzians = nl;
+    if (n_peaks) *n_peaks = np;
+}
+
+extern "C" mdb_status mdb_batch_export(const mdb_batch *b, int32_t *status, uint64_t *n_lorentzians, uint64_t *n_peaks,
+                                       double *mse, mdb_lorentzian *lorentzians, int32_t *peaks)
+{
+    if (!b) return fail(MDB_ERR_INVALID_ARGUMENT, "mdb_batch_export: null batch");
+    size_t ol = 0, op = 0;
+    for (size_t i = 0; i < b->r.size(); ++i) {
+        const SpecResult &r = b->r[i];
+        if (status) status[i] = r.status;
+        if (n_lorentzians) n_lorentzians[i] = r.lor.size();
+        if (n_peaks) n_peaks[i] = r.peaks.size() / 3;
+        if (mse) mse[i] = r.mse;
+        if (lorentzians && !r.lor.empty()) std::memcpy(lorentzians + ol, r.lor.data(), r.lor.size() * sizeof(mdb_lorentzian));
+        if (peaks && !r.peaks.empty()) std::memcpy(peaks + 3 * op, r.peaks.data(), r.peaks.size() * sizeof(int32_t));
+        ol += r.lor.size();
+        op += r.peaks.size() / 3;
+    }
+    return MDB_OK;
+}
+
 static const char *status_text(int st)
 {
     switch (st) {

@@ -120,17 +120,20 @@ class Deconvoluter:
         try:
             raise_for_status(st, _lib.last_error())
             sm, se, fi = self.smoothing_settings(), self.selection_settings(), self.fitting_settings()
-            out = []
-            for i in range(n):
-                k = lib.mdb_batch_n_lorentzians(batch, i)
-                params = np.empty((k, 3), dtype=np.float64)
-                if k:
-                    C.memmove(params.ctypes.data, lib.mdb_batch_lorentzians(batch, i), k * 24)
-                p = lib.mdb_batch_n_peaks(batch, i)
-                peaks = np.empty((p, 3), dtype=np.int32)
-                if p:
-                    C.memmove(peaks.ctypes.data, lib.mdb_batch_peaks(batch, i), p * 12)
-                out.append(Deconvolution(params, lib.mdb_batch_mse(batch, i), sm, se, fi, peaks))
+            # one bulk export for the whole batch; every Deconvolution holds views into the flat arrays
+            tot_l, tot_p = C.c_size_t(), C.c_size_t()
+            lib.mdb_batch_totals(batch, C.byref(tot_l), C.byref(tot_p))
+            n_lor = np.empty(n, dtype=np.uint64)
+            n_pk = np.empty(n, dtype=np.uint64)
+            mse = np.empty(n, dtype=np.float64)
+            params = np.empty((tot_l.value, 3), dtype=np.float64)
+            peaks = np.empty((tot_p.value, 3), dtype=np.int32)
+            raise_for_status(lib.mdb_batch_export(batch, None, n_lor.ctypes.data, n_pk.ctypes.data, mse.ctypes.data,
+                                                  params.ctypes.data, peaks.ctypes.data), _lib.last_error())
+            ol = np.concatenate(([0], np.cumsum(n_lor))).astype(np.int64)
+            op = np.concatenate(([0], np.cumsum(n_pk))).astype(np.int64)
+            out = [Deconvolution(params[ol[i]:ol[i + 1]], float(mse[i]), sm, se, fi, peaks[op[i]:op[i + 1]])
+                   for i in range(n)]
             return out
         finally:
             if batch:

@@ -134,6 +134,16 @@ extern "C" {
     pub fn mdb_batch_n_peaks(b: *const mdb_batch, i: usize) -> usize;
     pub fn mdb_batch_peaks(b: *const mdb_batch, i: usize) -> *const i32;
     pub fn mdb_batch_free(b: *mut mdb_batch);
+    pub fn mdb_batch_totals(b: *const mdb_batch, n_lorentzians: *mut usize, n_peaks: *mut usize);
+    pub fn mdb_batch_export(
+        b: *const mdb_batch,
+        status: *mut i32,
+        n_lorentzians: *mut u64,
+        n_peaks: *mut u64,
+        mse: *mut f64,
+        lorentzians: *mut mdb_lorentzian,
+        peaks: *mut i32,
+    ) -> mdb_status;
 
     pub fn mdb_deconvolute_spectra(
         d: *const mdb_deconvoluter,
