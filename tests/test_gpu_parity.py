@@ -544,6 +544,37 @@ def test_batch_mixed_lengths_settings_and_order():
     _check_e2e(dec, O.Settings(selection_kind=O.SELECT_DETECTOR_ONLY, fitting_iterations=2), specs[1:2], "detector only")
 
 
+def test_increasing_axis_and_ignore_regions():
+    """The reference accepts either axis direction (meta/monotonicity.rs); Spectrum::new orders the
+    signal boundaries to the axis (spectrum.rs:854-863) and the index helpers use the signed step.
+    An increasing axis is the decreasing one read backwards."""
+    n = 32768
+    xd = synth.axis(n)
+    yd = synth.config3(21, n=n, x=xd)
+    xi, yi = xd[::-1].copy(), yd[::-1].copy()
+    sp = Spectrum(xi, yi, (11.8, -2.2))          # given in the "wrong" order on purpose
+    assert sp.signal_boundaries == (-2.2, 11.8)
+    dec = Deconvoluter()
+    _check_e2e(dec, O.Settings(), [sp], "increasing axis")
+    dec.add_ignore_region((4.9, 4.7))
+    dec.add_ignore_region((7.0, 7.5))
+    dec.add_ignore_region((7.4, 8.0))            # merges with the previous one (deconvoluter.rs:438-472)
+    assert dec.ignore_regions() == [(4.7, 4.9), (7.0, 8.0)]
+    settings = O.Settings(ignore_regions=[(4.7, 4.9), (7.0, 8.0)])
+    _check_e2e(dec, settings, [sp], "increasing axis with two ignore regions")
+    # The same two regions on a DECREASING axis: the reference builds its MSE ranges from the regions in
+    # ppm order (deconvoluter.rs:828-845), whose indices then run backwards, and the slice
+    # `superpositions[start..end]` panics.  The library reports exactly that instead of inventing a result.
+    spd = Spectrum(xd, yd, (-2.2, 11.8))
+    r = O.deconvolute_spectrum(settings, spd.chemical_shifts, spd.intensities, spd.signal_boundaries)
+    assert r.status == O.PANIC
+    with pytest.raises(exceptions.UnexpectedError, match="reference implementation panics"):
+        dec.deconvolute_spectrum(spd)
+    dec.clear_ignore_regions()
+    dec.add_ignore_region((4.7, 4.9))            # a single region is fine in either direction
+    _check_e2e(dec, O.Settings(ignore_regions=[(4.7, 4.9)]), [spd, sp], "one ignore region, both directions")
+
+
 def test_batch_spanning_several_chunks(monkeypatch):
     monkeypatch.setenv("MDB_CHUNK_SPECTRA", "3")
     n = 8192
