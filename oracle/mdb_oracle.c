@@ -9,8 +9,9 @@
  * so this file is a scalar-f64 restatement of the reference's arithmetic, in the
  * reference's operation order, built with -ffp-contract=off (rustc never contracts to FMA).
  * It is PINNED against every known-answer unit test the reference holds for this path
- * (tests/test_oracle_kats.py lists them with file:line) and against the survey's
- * independent NumPy checkpoints on blood_01.  END-TO-END PARITY IS UNPINNED: the
+ * (tests/test_oracle_kats.py lists them with file:line), against the survey's independent
+ * NumPy checkpoints on blood_01, and against a second restatement written separately in NumPy
+ * (oracle/numpy_restatement.py; bit-for-bit agreement on sim_01, blood_01 and synthetic spectra).  END-TO-END PARITY IS UNPINNED: the
  * reference commits no golden deconvolution output (metabodecon/tests/deconvoluter.rs
  * only writes JSON to a temp dir), so there is nothing end-to-end to pin against.
  *

@@ -215,3 +215,43 @@ def test_optimize_settings_grid_and_argmin(sim_arrays):  # deconvoluter.rs:761-8
     k = int(np.argmin(all_mse))  # numpy argmin returns the first minimum, like Iterator::min_by
     assert best == want[k][0] and mse == want[k][1]
     assert 5.0 <= best[2] <= 8.0 and best[3] in (5, 10, 15)
+
+
+# ------------------------------------------------------------------------------------------------
+# Two independent restatements (C: oracle/mdb_oracle.c, NumPy: oracle/numpy_restatement.py) must agree
+# bit for bit -- the strongest pin available without a Rust toolchain.
+# ------------------------------------------------------------------------------------------------
+def _bits(a):
+    return np.ascontiguousarray(a, dtype=np.float64).view(np.uint64)
+
+
+def _agree(x, y, sb, ignore, what):
+    from oracle import numpy_restatement as NR
+    sb = tuple(sb)
+    got = NR.deconvolute(x, y, sb, ignore_regions=ignore)
+    want = O.deconvolute_spectrum(O.Settings(ignore_regions=ignore), x, y, sb)
+    assert want.status == O.OK
+    assert np.array_equal(_bits(got["smoothed"]), _bits(want.smoothed)), f"{what}: smoothing"
+    assert np.array_equal(got["peaks"], want.peaks.astype(np.int64)), f"{what}: selected peaks"
+    assert _bits([got["mean"], got["sd"]]).tolist() == _bits([want.mean, want.sd]).tolist(), f"{what}: mean/sd"
+    assert got["lorentzians"].shape == want.lorentzians.shape, f"{what}: retained count"
+    assert np.array_equal(_bits(got["lorentzians"]), _bits(want.lorentzians)), f"{what}: lorentzians"
+    assert _bits([got["mse"]]).tolist() == _bits([want.mse]).tolist(), f"{what}: mse"
+
+
+def test_numpy_and_c_restatements_agree_sim(sim_arrays):
+    x, y = sim_arrays
+    _agree(x, y, (3.55, 3.35) if x[0] > x[1] else (3.35, 3.55), None, "sim_01")
+
+
+def test_numpy_and_c_restatements_agree_blood(blood_arrays):
+    x, y = blood_arrays
+    _agree(x, y, (11.8, -2.2), [(4.7, 4.9)], "blood_01 with the water region ignored")
+
+
+def test_numpy_and_c_restatements_agree_synthetic():
+    import synth
+    n = 16384
+    x = synth.axis(n)
+    _agree(x, synth.config3(3, n=n, x=x), synth.SIGNAL_BOUNDARIES, None, "synthetic f64")
+    _agree(x, synth.config3(4, n=n, x=x, integer=True), synth.SIGNAL_BOUNDARIES, [(1.0, 1.2)], "synthetic integer")
