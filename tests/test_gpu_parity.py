@@ -807,3 +807,44 @@ def test_c_host_program_through_the_abi(golden_dir, tmp_path):
     assert float.fromhex(first[7]) == float.fromhex("0x1.0808a64fe177ep+35")
     l0 = out.splitlines()[1].split()
     assert float.fromhex(l0[2]) == float.fromhex("0x1.084fd4b50b8dfp-4") and float.fromhex(l0[6]) == float.fromhex("0x1.0eac0d0cd9679p+3")
+
+
+# ------------------------------------------------------------------------------ randomised differential
+def test_randomised_differential_gpu_vs_oracle():
+    """120 random spectra (integer / float values, flat stretches, 200..6000 points) under random
+    settings, in random-size batches: the GPU result must equal the oracle's in bits, and error
+    statuses must agree."""
+    from test_oracle_kats import _random_spectrum
+    rng = np.random.default_rng(777)
+    done = 0
+    while done < 120:
+        batch = int(rng.integers(1, 9))
+        iters, window = int(rng.integers(1, 6)), int(rng.choice([2, 3, 4, 5, 7, 9, 11]))
+        thr, fit = float(rng.uniform(0.5, 8.0)), int(rng.integers(1, 12))
+        dec = Deconvoluter()
+        dec.set_moving_average_smoother(iters, window)
+        dec.set_noise_score_selector(thr)
+        dec.set_analytical_fitter(fit)
+        settings = O.Settings(smoothing_iterations=iters, smoothing_window=window, threshold=thr, fitting_iterations=fit)
+        specs, wants = [], []
+        for _ in range(batch):
+            n = int(rng.integers(200, 6000))
+            x, y = _random_spectrum(rng, n)
+            sb = (float(rng.uniform(7.0, 9.5)), float(rng.uniform(-1.5, 1.0)))
+            sp = Spectrum(x, y, sb)
+            specs.append(sp)
+            wants.append(O.deconvolute_spectrum(settings, x, y, sp.signal_boundaries))
+        first_bad = next((w.status for w in wants if w.status != O.OK), O.OK)
+        if first_bad != O.OK:
+            with pytest.raises(Exception):
+                dec.deconvolute_spectra(specs)
+            done += batch
+            continue
+        outs = dec.deconvolute_spectra(specs)
+        for i, (out, w) in enumerate(zip(outs, wants)):
+            what = f"random case {done + i} (iters={iters}, window={window}, thr={thr:.3f}, fit={fit})"
+            assert np.array_equal(out.peaks.astype(np.int64), w.peaks.astype(np.int64)), what
+            nan = np.isnan(w.lorentzians)
+            assert_bit_equal(np.where(nan, 0.0, out.parameters), np.where(nan, 0.0, w.lorentzians), what)
+            assert out.mse == w.mse or (np.isnan(out.mse) and np.isnan(w.mse)), what
+        done += batch

@@ -255,3 +255,47 @@ def test_numpy_and_c_restatements_agree_synthetic():
     x = synth.axis(n)
     _agree(x, synth.config3(3, n=n, x=x), synth.SIGNAL_BOUNDARIES, None, "synthetic f64")
     _agree(x, synth.config3(4, n=n, x=x, integer=True), synth.SIGNAL_BOUNDARIES, [(1.0, 1.2)], "synthetic integer")
+
+
+def _random_spectrum(rng, n):
+    """Random small spectrum with the features that stress the path: integer values (exact ties in
+    d2), flat stretches, narrow and wide Lorentzians, noise."""
+    x = 10.0 - np.arange(n) * (12.0 / (n - 1))
+    y = rng.normal(0.0, 30.0, n)
+    for _ in range(int(rng.integers(3, 25))):
+        m, hw, a = rng.uniform(-1.5, 9.5), np.exp(rng.uniform(np.log(3e-3), np.log(8e-2))), np.exp(rng.uniform(np.log(2e3), np.log(1e6)))
+        y += a * hw * hw / (hw * hw + (x - m) ** 2)
+    if rng.random() < 0.5:
+        y = np.rint(y)
+    if rng.random() < 0.3:
+        lo = int(rng.integers(0, n - 40))
+        y[lo:lo + int(rng.integers(5, 40))] = np.rint(y[lo])
+    return x, y
+
+
+def test_randomised_differential_c_vs_numpy():
+    """40 random spectra x random settings: every stage of the two restatements must agree in bits
+    (or both report the same error condition)."""
+    from oracle import numpy_restatement as NR
+    rng = np.random.default_rng(20261018)
+    checked = 0
+    for case in range(40):
+        n = int(rng.integers(200, 3000))
+        x, y = _random_spectrum(rng, n)
+        iters, window = int(rng.integers(1, 6)), int(rng.choice([2, 3, 4, 5, 7, 9]))
+        thr, fit = float(rng.uniform(0.5, 8.0)), int(rng.integers(1, 12))
+        sb = (float(rng.uniform(7.0, 9.5)), float(rng.uniform(-1.5, 1.0)))
+        want = O.deconvolute_spectrum(O.Settings(smoothing_iterations=iters, smoothing_window=window, threshold=thr,
+                                                 fitting_iterations=fit), x, y, sb)
+        sm = NR.smooth_values(y, iters, window)
+        assert np.array_equal(_bits(sm), _bits(want.smoothed)), f"case {case}: smoothing ({iters}, {window})"
+        if want.status != O.OK:
+            continue
+        got = NR.deconvolute(x, y, sb, smoothing=(iters, window), threshold=thr, fit_iterations=fit)
+        assert np.array_equal(got["peaks"], want.peaks.astype(np.int64)), f"case {case}: peaks"
+        assert got["lorentzians"].shape == want.lorentzians.shape, f"case {case}: retained"
+        assert np.array_equal(_bits(got["lorentzians"]), _bits(want.lorentzians)), f"case {case}: lorentzians"
+        a, b = _bits([got["mse"]])[0], _bits([want.mse])[0]
+        assert a == b or (np.isnan(got["mse"]) and np.isnan(want.mse)), f"case {case}: mse"
+        checked += 1
+    assert checked >= 25
