@@ -1100,7 +1100,7 @@ static size_t chunk_size_for(const std::vector<HostSpec> &hs)
     if (env && std::atoi(env) > 0) return (size_t)std::atoi(env);
     // About 2^23 points per chunk (64 spectra of 2^17 points): small enough that eight chunks in
     // flight keep every SM busy through each other's kernel tails and host round trips, large
-    // enough that a fit-refinement launch still fills the GPU (measured: gpurun_out/depth_sweep*.log).
+    // enough that a fit-refinement launch still fills the GPU (measured: profiles/depth_sweep_r1_*.txt).
     const size_t per_spec = 48 * max_n + 4096;          // device bytes per spectrum
     const size_t budget = (size_t)1536 << 20;           // per workspace
     size_t c = std::min(budget / per_spec, ((size_t)1 << 23) / std::max<size_t>(max_n, 1));
@@ -1160,7 +1160,7 @@ static mdb_status run_pipeline(const mdb_deconvoluter &dc, const std::vector<Hos
     // from the first chunk's selected-peak counts so that a chunk carries about TARGET Lorentzian
     // evaluations (~12 ms of FP64 work): many-peak spectra get small chunks (fine-grained overlap
     // of kernel tails across streams), few-peak spectra get large ones (launch and smoothing
-    // latency amortised).  Measured in gpurun_out/depth_sweep*.log.
+    // latency amortised).  Measured in profiles/depth_sweep_r1_*.txt.
     const double TARGET_EVALS = 1.8e10;
     const bool pinned_size = std::getenv("MDB_CHUNK_SPECTRA") && std::atoi(std::getenv("MDB_CHUNK_SPECTRA")) > 0;
     const size_t csz_first = chunk_size_for(hs);
