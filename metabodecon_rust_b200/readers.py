@@ -28,8 +28,9 @@ _PROCS = {
 }
 
 
-class MissingMetadataError(ValueError):
-    pass
+from .exceptions import MalformedData, MalformedMetadata, MissingData, MissingMetadata  # noqa: E402
+
+MissingMetadataError = MissingMetadata  # the reference's spectrum::error::Kind::MissingMetadata
 
 
 def _extract(table, text, path):
@@ -38,7 +39,10 @@ def _extract(table, text, path):
         m = rx.search(text)
         if m is None:
             raise MissingMetadataError(f"missing metadata key '{key}' in {path}")
-        out[key] = conv(m.group(1))
+        try:
+            out[key] = conv(m.group(1))
+        except ValueError as err:
+            raise MalformedMetadata(f"malformed metadata key '{key}' in {path}: {err}") from err
     return out
 
 
@@ -59,12 +63,12 @@ def read_bruker_arrays(path: str, experiment: int, processing: int):
     if procs["data_type"] == 0:  # int32, scaled by 2^NC_proc (bruker.rs:459-475)
         raw = np.fromfile(one_r_path, dtype=np.dtype(order + "i4"), count=size)
         if raw.size != size:
-            raise ValueError(f"{one_r_path}: expected {size} values, found {raw.size}")
+            raise MissingData(f"{one_r_path}: expected {size} values, found {raw.size}")
         intensities = raw.astype(np.float64) * (2.0 ** procs["exponent"])
     else:  # f64 (bruker.rs:476-487)
         raw = np.fromfile(one_r_path, dtype=np.dtype(order + "f8"), count=size)
         if raw.size != size:
-            raise ValueError(f"{one_r_path}: expected {size} values, found {raw.size}")
+            raise MissingData(f"{one_r_path}: expected {size} values, found {raw.size}")
         intensities = raw.astype(np.float64)
     meta = {"nucleus": acqus["nucleus"], "frequency": acqus["frequency"]}
     return chemical_shifts, intensities, meta
@@ -127,7 +131,7 @@ def _decode_xydata(data: str, path: str) -> np.ndarray:
                 try:
                     out.append(float(tok))
                 except ValueError as err:
-                    raise ValueError(f"{path}: malformed value '{tok}'") from err
+                    raise MalformedData(f"{path}: malformed value '{tok}'") from err
         return np.asarray(out, dtype=np.float64)
     values = []
     prev_line_ended_in_dif = False
@@ -151,20 +155,20 @@ def _decode_xydata(data: str, path: str) -> np.ndarray:
                 mag = int(str(abs(d)) + tok[1:])
                 last_dif = -mag if d < 0 else mag
                 if not line_vals:
-                    raise ValueError(f"{path}: DIF token without a preceding ordinate")
+                    raise MalformedData(f"{path}: DIF token without a preceding ordinate")
                 line_vals.append(line_vals[-1] + last_dif)
                 last_kind = "dif"
             elif head in _DUP:
                 count = int(str(_DUP[head]) + tok[1:])
                 if not line_vals:
-                    raise ValueError(f"{path}: DUP token without a preceding ordinate")
+                    raise MalformedData(f"{path}: DUP token without a preceding ordinate")
                 for _ in range(count - 1):
                     line_vals.append(line_vals[-1] + last_dif if last_kind == "dif" else line_vals[-1])
             else:  # PAC (+/- prefixed) or a bare integer
                 try:
                     line_vals.append(int(tok))
                 except ValueError as err:
-                    raise ValueError(f"{path}: malformed value '{tok}'") from err
+                    raise MalformedData(f"{path}: malformed value '{tok}'") from err
                 last_kind = "abs"
         if prev_line_ended_in_dif and line_vals:
             line_vals = line_vals[1:]  # Y-check: repeats the last ordinate of the previous line
@@ -186,7 +190,7 @@ def read_jcampdx_arrays(path: str):
     block = _dx_capture(_DX_XY, dx, path)
     m = _DX_DATA.search(dx)
     if m is None or not m.group("v").strip():
-        raise ValueError(f"{path}: missing data table")
+        raise MissingData(f"{path}: missing data table")
     xunits = block["xunits"].upper()
     if xunits not in ("HZ", "PPM"):
         raise ValueError(f"{path}: unsupported x units {xunits}")
@@ -203,6 +207,6 @@ def read_jcampdx_arrays(path: str):
     chemical_shifts = offset + i * step
     intensities = _decode_xydata(m.group("v").strip(), path) * block["factor"]
     if intensities.size != size:
-        raise ValueError(f"{path}: expected {size} ordinates, decoded {intensities.size}")
+        raise MalformedData(f"{path}: expected {size} ordinates, decoded {intensities.size}")
     meta = {"nucleus": header["nucleus"].lstrip("^"), "frequency": header["frequency"]}
     return chemical_shifts, intensities, meta
