@@ -101,9 +101,12 @@ class ClockSampler:
             try:
                 sm.append(float(parts[0]))
                 mx.append(float(parts[1]))
-                pw.append(float(parts[2]))
             except ValueError:
                 continue
+            try:
+                pw.append(float(parts[2]))
+            except ValueError:
+                pass
             for name, val in zip(names, parts[3:7]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
