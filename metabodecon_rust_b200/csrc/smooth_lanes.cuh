@@ -228,7 +228,7 @@ smooth_lanes_kernel(const SpecDesc *__restrict__ sd, int n_spec, int iters)
             double cur[W], nxt[W];
 #pragma unroll
             for (int u = 0; u < W; ++u) { cur[u] = irow[u]; nxt[u] = 0.0; }
-#pragma unroll 2
+#pragma unroll 4
             for (int g = 0; g < T / W; ++g) {
                 if (g + 1 < T / W) {
 #pragma unroll
