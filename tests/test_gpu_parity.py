@@ -848,3 +848,37 @@ def test_randomised_differential_gpu_vs_oracle():
             assert_bit_equal(np.where(nan, 0.0, out.parameters), np.where(nan, 0.0, w.lorentzians), what)
             assert out.mse == w.mse or (np.isnan(out.mse) and np.isnan(w.mse)), what
         done += batch
+
+
+# ------------------------------------------------------------------------------ re-entrancy
+def test_concurrent_callers_share_one_deconvoluter():
+    """The reference's Deconvoluter is Send + Sync (deconvoluter.rs:913-917) and rayon calls it from
+    many workers at once; the C ABI must be re-entrant: four threads, one shared handle, different
+    batches, every result identical to the single-threaded one."""
+    import threading
+    n = 8192
+    x = synth.axis(n)
+    batches = [[Spectrum(x, synth.config3(900 + 10 * t + s, n=n, x=x), (-2.2, 11.8)) for s in range(5)] for t in range(4)]
+    dec = Deconvoluter()
+    dec.add_ignore_region((4.7, 4.9))
+    want = [dec.deconvolute_spectra(b) for b in batches]
+    got, errors = [None] * 4, []
+
+    def work(t):
+        try:
+            for _ in range(3):
+                got[t] = dec.deconvolute_spectra(batches[t])
+        except Exception as err:  # noqa: BLE001
+            errors.append(err)
+
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(4)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
+    for t in range(4):
+        for a, b in zip(want[t], got[t]):
+            assert np.array_equal(a.peaks, b.peaks)
+            assert_bit_equal(b.parameters, a.parameters, f"thread {t}")
+            assert a.mse == b.mse
