@@ -139,7 +139,8 @@ enum {
     MDB_KERNEL_MSE_SUPERPOSITION = 6,
     MDB_KERNEL_MSE_REDUCE = 7,
     MDB_KERNEL_SUPERPOSITION_VEC = 8,
-    MDB_KERNEL_COUNT = 9
+    MDB_KERNEL_SMALL_FUSED = 9,
+    MDB_KERNEL_COUNT = 10
 };
 void mdb_profile_enable(int on);
 void mdb_profile_reset(void);

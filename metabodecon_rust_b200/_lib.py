@@ -36,7 +36,7 @@ MDB_SCORING_MINIMUM_SUM = 0
 MDB_FITTING_ANALYTICAL = 0
 MDB_MEM_HOST, MDB_MEM_DEVICE = 0, 1
 KERNEL_NAMES = ["smooth", "detect", "select", "fit_init", "fit_iter", "retain", "mse_superposition",
-                "mse_reduce", "superposition_vec"]
+                "mse_reduce", "superposition_vec", "small_fused"]
 
 
 class Lorentzian3(C.Structure):

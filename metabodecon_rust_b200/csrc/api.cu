@@ -8,6 +8,7 @@
 #include "../../include/mdb200.h"
 #include "kernels.cuh"
 #include "smooth_lanes.cuh"
+#include "small_fused.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -465,12 +466,17 @@ struct Workspace {
     // stage B
     DevBuf fdesc, segs, fit_state, par_a, par_b, lor, n_kept, resid, mse, peaks_dense, fit_queue, blk_off;
     PinBuf h_fdesc, h_segs, h_lor, h_n_kept, h_mse, h_peaks, h_blk_off;
+    // small-spectrum path (run_small)
+    DevBuf small_in;
+    PinBuf h_small_in, h_small_out;
     void release()
     {
         for (DevBuf *b : {&x, &y, &ys, &tmp, &tile_cnt, &pk, &sc, &sfr, &sel, &ig, &desc, &sel_out, &fdesc,
-                          &segs, &fit_state, &par_a, &par_b, &lor, &n_kept, &resid, &mse, &peaks_dense, &fit_queue, &blk_off})
+                          &segs, &fit_state, &par_a, &par_b, &lor, &n_kept, &resid, &mse, &peaks_dense, &fit_queue, &blk_off,
+                          &small_in})
             b->release();
-        for (PinBuf *b : {&h_desc, &h_ig, &h_sel_out, &h_stage, &h_fdesc, &h_segs, &h_lor, &h_n_kept, &h_mse, &h_peaks, &h_blk_off})
+        for (PinBuf *b : {&h_desc, &h_ig, &h_sel_out, &h_stage, &h_fdesc, &h_segs, &h_lor, &h_n_kept, &h_mse, &h_peaks, &h_blk_off,
+                          &h_small_in, &h_small_out})
             b->release();
         if (ev_a) cudaEventDestroy(ev_a);
         if (ev_b) cudaEventDestroy(ev_b);
@@ -1229,6 +1235,190 @@ static mdb_status run_pipeline(const mdb_deconvoluter &dc, const std::vector<Hos
 }
 
 // ---------------------------------------------------------------------------------------------
+// Small spectra (every spectrum of the call <= SMALL_MAX_N points): small_fused.cuh.
+// Per chunk: one packed H2D copy (descriptors, index lists, x rows, y rows), the smoothing launch,
+// the fused launch, one stream synchronisation; the kernel stores its results straight into a
+// page-locked host slot per spectrum.  MDB_SMALL_PATH=0 sends such calls through the general
+// pipeline instead (tests compare the two).
+// ---------------------------------------------------------------------------------------------
+static bool small_path_applies(const std::vector<HostSpec> &hs)
+{
+    const char *env = std::getenv("MDB_SMALL_PATH");
+    if (env && env[0] == '0') return false;
+    if (hs.empty()) return false;
+    for (const HostSpec &h : hs) {
+        if (h.n > (size_t)SMALL_MAX_N || h.ys_dev) return false;
+        long long pts = 0;  // residual slots: the ranges of a valid spectrum are disjoint, but do not rely on it
+        for (auto &rg : h.ranges) pts += rg.second - rg.first;
+        if (pts > (long long)h.n) return false;
+    }
+    return true;
+}
+
+static mdb_status run_small(const mdb_deconvoluter &dc, const std::vector<HostSpec> &hs, int memory,
+                            std::vector<SpecResult> &results)
+{
+    const size_t n_spectra = hs.size();
+    size_t max_n = 0;
+    for (auto &h : hs) max_n = std::max(max_n, h.n);
+    const int n_al = (int)align_up(max_n, 8);
+    const int cap = n_al / 2;
+    const size_t slot = small_slot_bytes(cap);
+    const size_t smem = small_smem_bytes(n_al);
+    if ((int)smem + 1024 > smem_optin_limit()) return fail(MDB_ERR_UNSUPPORTED, "small path: shared memory limit");
+    const size_t row = (size_t)n_al;  // elements per x / y / ys row
+    size_t chunk_cap = std::min(((size_t)64 << 20) / slot, ((size_t)64 << 20) / (16 * row + 256));
+    chunk_cap = std::max<size_t>(1, chunk_cap);
+    const bool ma = dc.smoothing.kind == MDB_SMOOTHING_MOVING_AVERAGE;
+    // the moving average runs inside the fused kernel (one warp, one lane per pass) unless it has
+    // more passes than a warp has lanes; MDB_SMALL_SMOOTH=separate keeps it a launch of its own
+    const char *sm_env = std::getenv("MDB_SMALL_SMOOTH");
+    const bool smooth_fused = ma && dc.smoothing.iterations <= (uint64_t)SMALL_SMOOTH_MAX_ITERS
+                              && dc.smoothing.window_size <= (uint64_t)SMALL_MAX_N && !(sm_env && sm_env[0] == 's');
+    const bool need_tmp = ma && !smooth_fused && dc.smoothing.iterations >= 2;
+
+    Workspace *wsp = nullptr;
+    mdb_status st = acquire_workspace(&wsp);
+    if (st != MDB_OK) return st;
+    Workspace &ws = *wsp;
+    struct Releaser { Workspace *w; ~Releaser() { cudaStreamSynchronize(w->stream); release_workspace(w); } } releaser{wsp};
+    CUDA_TRY(cudaFuncSetAttribute(small_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+
+    std::vector<SpecDesc> descs;
+    std::vector<ProfSpan> spans;
+    for (size_t first = 0; first < n_spectra; first += chunk_cap) {
+        const size_t S = std::min(chunk_cap, n_spectra - first);
+        // ---- layout of the packed input blob (same offsets on the host and on the device)
+        size_t int_elems = 0;
+        std::vector<size_t> ig_off(S), rg_off(S);
+        std::map<const double *, size_t> x_map;  // caller x pointer -> row index
+        for (size_t s = 0; s < S; ++s) {
+            const HostSpec &h = hs[first + s];
+            ig_off[s] = int_elems; int_elems += h.ig.size();
+            rg_off[s] = int_elems; int_elems += 2 * h.ranges.size();
+            if (memory == MDB_MEM_HOST && !x_map.count(h.x)) { const size_t k = x_map.size(); x_map[h.x] = k; }
+        }
+        const size_t off_small = align_up(S * sizeof(SpecDesc), 16);
+        const size_t off_int = off_small + align_up(S * sizeof(SmallDesc), 16);
+        const size_t off_x = off_int + align_up(int_elems * 4, 16);
+        const size_t off_y = off_x + x_map.size() * row * 8;
+        const size_t in_bytes = (memory == MDB_MEM_HOST) ? off_y + S * row * 8 : off_x;
+        CUDA_TRY(ws.small_in.ensure(in_bytes));
+        CUDA_TRY(ws.h_small_in.ensure(in_bytes));
+        CUDA_TRY(ws.h_small_out.ensure(S * slot));
+        if (ma && !smooth_fused) CUDA_TRY(ws.ys.ensure(S * row * 8));
+        if (need_tmp) CUDA_TRY(ws.tmp.ensure(S * row * 8));
+        CUDA_TRY(ws.fit_state.ensure(S * 14 * (size_t)cap * 8));
+        unsigned char *out_dev = nullptr;  // device-side address of the page-locked result slots
+        CUDA_TRY(cudaHostGetDevicePointer((void **)&out_dev, ws.h_small_out.p, 0));
+
+        unsigned char *hb = ws.h_small_in.as<unsigned char>();
+        unsigned char *db = ws.small_in.as<unsigned char>();
+        SpecDesc *h_desc = reinterpret_cast<SpecDesc *>(hb);
+        SmallDesc *h_small = reinterpret_cast<SmallDesc *>(hb + off_small);
+        int *h_int = reinterpret_cast<int *>(hb + off_int);
+        const int *d_int = reinterpret_cast<const int *>(db + off_int);
+        descs.assign(S, SpecDesc{});
+        for (size_t s = 0; s < S; ++s) {
+            const HostSpec &h = hs[first + s];
+            SpecDesc &d = descs[s];
+            if (memory == MDB_MEM_HOST) {
+                d.x = reinterpret_cast<const double *>(db + off_x) + x_map[h.x] * row;
+                d.y = reinterpret_cast<const double *>(db + off_y) + s * row;
+                std::memcpy(hb + off_y + s * row * 8, h.y, h.n * 8);
+            } else {
+                d.x = h.x;
+                d.y = h.y;
+            }
+            // Identity (smoothing/identity.rs) and the fused moving average read the raw row
+            d.ys = (ma && !smooth_fused) ? ws.ys.as<double>() + s * row : const_cast<double *>(d.y);
+            d.tmp = need_tmp ? ws.tmp.as<double>() + s * row : nullptr;
+            d.pk = nullptr; d.sc = nullptr; d.tile_cnt = nullptr; d.sfr = nullptr; d.sel = nullptr;
+            d.ig = d_int + ig_off[s];
+            d.n = (int)h.n;
+            d.n_tiles = 0;
+            d.sb0 = h.sb_i0; d.sb1 = h.sb_i1;
+            d.n_ig = (int)(h.ig.size() / 2);
+            d.has_ig = dc.has_ignore ? 1 : 0;
+            d.threshold = h.threshold;
+            for (size_t q = 0; q < h.ig.size(); ++q) h_int[ig_off[s] + q] = h.ig[q];
+            for (size_t q = 0; q < h.ranges.size(); ++q) {
+                h_int[rg_off[s] + 2 * q] = h.ranges[q].first;
+                h_int[rg_off[s] + 2 * q + 1] = h.ranges[q].second;
+            }
+            SmallDesc &e = h_small[s];
+            e.ranges = d_int + rg_off[s];
+            e.fit_state = ws.fit_state.as<double>() + s * 14 * (size_t)cap;
+            e.out = out_dev + s * slot;
+            e.n_ranges = (int)h.ranges.size();
+            e.n_iters = h.fit_iters;
+            e.cap = cap;
+            e.skip = (h.pre_status != MDB_OK) ? 1 : 0;
+        }
+        std::memcpy(h_desc, descs.data(), S * sizeof(SpecDesc));
+        if (memory == MDB_MEM_HOST)
+            for (auto &kv : x_map) {
+                size_t n = 0;
+                for (size_t s = 0; s < S; ++s)
+                    if (hs[first + s].x == kv.first) { n = hs[first + s].n; break; }
+                std::memcpy(hb + off_x + kv.second * row * 8, kv.first, n * 8);
+            }
+        CUDA_TRY(counted_memcpy_async(db, hb, in_bytes, cudaMemcpyHostToDevice, ws.stream));
+
+        const SpecDesc *d_desc = reinterpret_cast<const SpecDesc *>(db);
+        if (ma && !smooth_fused) {
+            st = launch_smooth(ws.stream, d_desc, descs, (int)dc.smoothing.iterations, (int)dc.smoothing.window_size, &spans);
+            if (st != MDB_OK) return st;
+        }
+        long long *d_stamps = nullptr;  // MDB_SMALL_STAMPS=1: phase clock of CTA 0, printed to stderr (development aid)
+        const char *stamps_env = std::getenv("MDB_SMALL_STAMPS");
+        if (stamps_env && stamps_env[0] == '1') {
+            CUDA_TRY(ws.blk_off.ensure(16 * 8));
+            CUDA_TRY(cudaMemsetAsync(ws.blk_off.p, 0, 16 * 8, ws.stream));
+            d_stamps = ws.blk_off.as<long long>();
+        }
+        prof_begin(&spans, MDB_KERNEL_SMALL_FUSED, ws.stream);
+        small_fused_kernel<<<(unsigned)S, SMALL_THREADS, smem, ws.stream>>>(
+            d_desc, reinterpret_cast<const SmallDesc *>(db + off_small), n_al, dc.selection.kind,
+            smooth_fused ? (int)dc.smoothing.iterations : 0, (int)dc.smoothing.window_size, d_stamps);
+        LAUNCH_CHECK();
+        prof_end(&spans, ws.stream, (double)S);
+        CUDA_TRY(cudaStreamSynchronize(ws.stream));
+        prof_resolve(&spans);
+        if (d_stamps) {
+            long long h[16];
+            CUDA_TRY(cudaMemcpy(h, d_stamps, sizeof(h), cudaMemcpyDeviceToHost));
+            static const char *names[] = {"smooth", "centres", "borders", "select", "fit_init", "fit_iters", "retain+mse", "fold"};
+            std::fprintf(stderr, "[mdb small stamps, cycles]");
+            for (int k = 1; k <= 8 && h[k] > 0; ++k) std::fprintf(stderr, " %s=%lld", names[k - 1], h[k] - h[k - 1]);
+            std::fprintf(stderr, "\n");
+        }
+
+        // ---- unpack the result slots
+        size_t out_bytes = 0;
+        for (size_t s = 0; s < S; ++s) {
+            const HostSpec &h = hs[first + s];
+            SpecResult &r = results[first + s];
+            if (h.pre_status != MDB_OK) { r.status = h.pre_status; continue; }
+            const unsigned char *sl = ws.h_small_out.as<unsigned char>() + s * slot;
+            const SmallOut *o = reinterpret_cast<const SmallOut *>(sl);
+            r.info = o->info;
+            r.status = o->info.status;
+            out_bytes += sizeof(SmallOut);
+            if (r.status != MDB_OK) continue;
+            const mdb_lorentzian *lor = reinterpret_cast<const mdb_lorentzian *>(sl + 64);
+            const int32_t *pk = reinterpret_cast<const int32_t *>(sl + 64 + (size_t)24 * cap);
+            r.lor.assign(lor, lor + o->n_kept);
+            r.peaks.assign(pk, pk + 3 * (size_t)o->info.n_selected);
+            r.mse = o->mse;
+            out_bytes += (size_t)24 * o->n_kept + (size_t)12 * o->info.n_selected;
+        }
+        count_transfer(out_bytes, cudaMemcpyDeviceToHost);  // written by the kernel over PCIe (zero-copy stores)
+    }
+    return MDB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // In-process multi-GPU sharding (host-memory batches only)
 // ---------------------------------------------------------------------------------------------
 static std::atomic<int> g_device_policy{1};  // 1 = the calling thread's current device; 0 = all visible; n = first n
@@ -1325,8 +1515,10 @@ extern "C" mdb_status mdb_deconvolute_spectra(const mdb_deconvoluter *d, const m
     if ((st = build_host_specs(*d, spectra, n_spectra, memory, hs)) != MDB_OK) return st;
 
     const int n_dev = (memory == MDB_MEM_HOST) ? devices_to_use(n_spectra) : 1;
+    const bool small = small_path_applies(hs);
+    auto run = small ? run_small : run_pipeline;
     if (n_dev <= 1) {
-        st = run_pipeline(*d, hs, memory, batch->r);
+        st = run(*d, hs, memory, batch->r);
     } else {
         // One host thread per GPU, contiguous shards, no exchange: the in-process form of the
         // one-process-per-GPU sharding.  Device d of the shard list is CUDA device d.
@@ -1343,7 +1535,7 @@ extern "C" mdb_status mdb_deconvolute_spectra(const mdb_deconvoluter *d, const m
                 }
                 std::vector<HostSpec> shard(hs.begin() + lo, hs.begin() + hi);
                 std::vector<SpecResult> res(hi - lo);
-                sts[dev] = run_pipeline(*d, shard, memory, res);
+                sts[dev] = run(*d, shard, memory, res);
                 if (sts[dev] != MDB_OK) msgs[dev] = g_last_error;  // thread-local in the worker
                 for (size_t i = lo; i < hi; ++i) batch->r[i] = std::move(res[i - lo]);
             });

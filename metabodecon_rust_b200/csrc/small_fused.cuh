@@ -1,0 +1,551 @@
+// small_fused.cuh -- the whole deconvolution of a SMALL spectrum in ONE launch.
+//
+// The chunked pipeline of api.cu (detect -> select -> host round trip -> fit_init -> fit_iter x I_f
+// -> retain -> superposition -> mse_reduce) is built for batches of 2^17-point spectra: ~20 launches
+// and two host synchronisations per chunk, which is all a 2 048-point spectrum (the reference's
+// `sim` bench set, benches/deconvoluter.rs:8-52) ever pays for.  Here one CTA owns one spectrum and
+// walks the same stages back to back with the whole second difference resident in shared memory:
+// no tiles, no halos, no cold fallbacks, no counts travelling to the host between stages; results
+// go straight into a page-locked host slot (zero-copy stores), so the call is one H2D copy, this
+// launch and one stream synchronisation.
+//
+// Arithmetic is the same as the big kernels', operation for operation (same helpers where they
+// exist), and every ordered sum is still a left fold: results are bit-identical to the general
+// path and to the oracle (tests/test_gpu_parity.py::test_small_*).
+//
+// Reference: peak_selection/common.rs:5-40, detector.rs:99-164, scorer.rs:65-74,
+// noise_score_filter.rs:32-54, 91-138, detector_only.rs:16-39, fitter_analytical.rs:19-72, 147-172,
+// peak_stencil.rs:113-131, lorentzian.rs:546-548, 606-635, deconvoluter.rs:828-862.
+#pragma once
+#include "kernels.cuh"
+
+namespace mdb {
+
+constexpr int SMALL_MAX_N = 4096;     // longest spectrum the fused kernel takes
+constexpr int SMALL_THREADS = 256;
+constexpr int SMALL_WARPS = SMALL_THREADS / 32;
+constexpr int SMALL_R = 4;            // points per thread in the MSE superposition
+
+// Shared-memory map, in bytes, N = the launch's longest spectrum rounded up to a multiple of 8
+// (cap = N/2 bounds the number of centres: two adjacent points can never both be centres):
+//   selection phase                                  fit / MSE phase
+//   [ 0, 6N)  sel   selected (l,c,r) triples          sel (kept for nothing but the order of writes)
+//   [6N,14N)  d2    second difference                 [6N,18N)  parameter buffer A (cap x 24 B)
+//   [14N,20N) pk    per-centre (l,c,r)                [18N,30N) parameter buffer B
+//   [20N,24N) sc    per-centre score                  residuals of the MSE overlay the dead buffer
+//   [24N,28N) sfr   dense ordered SFR scores
+//   [28N,30N) cen   centre list, then rank/flag per centre
+// and before any of that, while the spectrum is smoothed: [14N,22N) and [22N,30N) are the two
+// ping-pong rows of the moving average (the last pass leaves its row for the second difference).
+__host__ __device__ inline size_t small_smem_bytes(int n_al) { return (size_t)30 * n_al; }
+
+struct SmallDesc {
+    const int *ranges;      // MSE ranges of this spectrum, (start, end) pairs (deconvoluter.rs:829-845)
+    double *fit_state;      // 14 * cap doubles of scratch: stencils and superposition values per peak
+    unsigned char *out;     // result slot in mapped host memory: SmallOut, lor[cap], peaks[3 * cap]
+    int n_ranges, n_iters, cap, skip;
+};
+
+struct SmallOut {           // header of a result slot (64 bytes)
+    SelectOut info;
+    int n_kept, pad_;
+    double mse;
+};
+
+__host__ __device__ inline size_t small_slot_bytes(int cap) { return ((size_t)64 + (size_t)36 * cap + 63) & ~(size_t)63; }
+
+// Order-preserving compaction of the indices of [begin, end) for which pred holds: emit(i, rank)
+// is called once per kept index with its rank in ascending index order.  Every warp owns one
+// contiguous run; ranks come from ballot/popc inside the run plus the counts of the runs before
+// it.  pred is evaluated twice per index and must not depend on what emit writes for OTHER
+// indices.  All threads of the CTA must call; returns the number kept.
+template <class Pred, class Emit>
+__device__ __forceinline__ int small_ordered_compact(int begin, int end, int *warp_cnt, Pred pred, Emit emit)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    int seg = (end - begin + SMALL_WARPS - 1) / SMALL_WARPS;
+    seg = (seg + 31) & ~31;
+    const int b = begin + wid * seg, e = min(end, b + seg);
+    int cnt = 0;
+    for (int i0 = b; i0 < e; i0 += 32) {
+        const int i = i0 + lane;
+        const bool f = i < e && pred(i);
+        cnt += __popc(__ballot_sync(0xffffffffu, f));
+    }
+    if (lane == 0) warp_cnt[wid] = cnt;
+    __syncthreads();
+    int base = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < SMALL_WARPS; ++w) {
+        if (w < wid) base += warp_cnt[w];
+        tot += warp_cnt[w];
+    }
+    for (int i0 = b; i0 < e; i0 += 32) {
+        const int i = i0 + lane;
+        const bool f = i < e && pred(i);
+        const unsigned bal = __ballot_sync(0xffffffffu, f);
+        if (f) emit(i, base + __popc(bal & lt_mask));
+        base += __popc(bal);
+    }
+    __syncthreads();
+    return tot;
+}
+
+// U consecutive Lorentzians (AoS triples at p) at ONE point, fast-domain division: the U
+// quotients are independent and interleave stage by stage (what lorentz_step does across points),
+// then join the running sum in index order -- the same operations per element as lorentz_step.
+template <int U>
+__device__ __forceinline__ void lorentz_multi(const double *p, const double x, double &acc)
+{
+    double a[U], den[U], r[U], e[U], q[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) { a[u] = p[3 * u]; den[u] = __dsub_rn(x, p[3 * u + 2]); }
+#pragma unroll
+    for (int u = 0; u < U; ++u) den[u] = __dmul_rn(den[u], den[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) den[u] = __dadd_rn(p[3 * u + 1], den[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) r[u] = rcp_seed(den[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) e[u] = fma(-den[u], r[u], 1.0);
+#pragma unroll
+    for (int u = 0; u < U; ++u) e[u] = fma(e[u], e[u], e[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) r[u] = fma(r[u], e[u], r[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) e[u] = fma(-den[u], r[u], 1.0);
+#pragma unroll
+    for (int u = 0; u < U; ++u) r[u] = fma(r[u], e[u], r[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) q[u] = __dmul_rn(a[u], r[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) e[u] = fma(-den[u], q[u], a[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) q[u] = fma(r[u], e[u], q[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) acc = __dadd_rn(acc, q[u]);
+}
+
+// Moving average of one spectrum by ONE warp (smoothing/moving_average.rs:53-83, the recurrence of
+// smooth_pass_generic_kernel): lane p runs pass p, Db blocks of SMALL_SMOOTH_U points behind lane
+// p-1, reading that lane's output row and writing the other row (pass p reads row p&1).  Every
+// pass is still the reference's sequential running sum -- two dependent additions per point -- but
+// the passes overlap, and a block's loads are issued together ahead of its chain.
+// Hazards: a lane reads indices up to i0+U-1+r, written by its producer at least
+// one iteration earlier when Db >= 2 + (r-1)/U; the lane behind it overwrites indices below
+// (mb-Db+1)U of the row this lane reads, which it no longer needs when (Db-1)U >= W-r.
+constexpr int SMALL_SMOOTH_U = 16;
+constexpr int SMALL_SMOOTH_MAX_ITERS = 32;
+
+__device__ __forceinline__ void small_smooth_warp(double *rows, int row_stride, int n, int iters, int w)
+{
+    constexpr int U = SMALL_SMOOTH_U;
+    const int lane = threadIdx.x & 31;
+    const int r = w / 2;
+    const int db = 1 + (max(r, w - r) + U - 1) / U;
+    const int n_blocks = (n + U - 1) / U;
+    const bool active = lane < iters;
+    // pass p reads row p&1 and writes the other one; plain indices into one array (no __restrict__:
+    // other lanes write what this one reads)
+    const int in_o = (lane & 1) * row_stride, out_o = row_stride - in_o;
+    double sum = 0.0, div = 1.0;
+    int len = 0;
+    const int rounds = n_blocks + (iters - 1) * db;
+    for (int b = 0; b < rounds; ++b) {
+        const int mb = b - lane * db;
+        if (active && mb >= 0 && mb < n_blocks) {
+            const int i0 = mb * U;
+            if (mb == 0) {
+                for (int k = 0; k < r && k < n; ++k) sum = __dadd_rn(sum, rows[in_o + k]);
+                len = n < w ? n : w;
+            }
+            if (i0 >= w - r && i0 + U <= n - r) {  // window full, no edge in this block
+                double a[U], q[U];
+                const double *pa = rows + in_o + i0 + r, *pq = pa - w;
+#pragma unroll
+                for (int u = 0; u < U; ++u) { a[u] = pa[u]; q[u] = pq[u]; }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    sum = __dadd_rn(sum, a[u]);
+                    sum = __dsub_rn(sum, q[u]);
+                    a[u] = __dmul_rn(sum, div);
+                }
+                double *po = rows + out_o + i0;
+#pragma unroll
+                for (int u = 0; u < U; ++u) po[u] = a[u];
+            } else {
+                for (int u = 0; u < U; ++u) {
+                    const int i = i0 + u;
+                    if (i >= n) break;
+                    if (i < n - r) {
+                        sum = __dadd_rn(sum, rows[in_o + i + r]);
+                        if (i + r >= w) sum = __dsub_rn(sum, rows[in_o + i + r - w]);
+                        else div = __ddiv_rn(1.0, (double)(i + r + 1));
+                        rows[out_o + i] = __dmul_rn(sum, div);
+                    } else if (len > 0) {
+                        sum = __dsub_rn(sum, rows[in_o + n - len]);
+                        --len;
+                        div = __ddiv_rn(1.0, (double)len);
+                        rows[out_o + i] = __dmul_rn(sum, div);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(SMALL_THREADS)
+small_fused_kernel(const SpecDesc *__restrict__ sd, const SmallDesc *__restrict__ xd, int n_al, int selector_kind,
+                   int smooth_iters, int smooth_window, long long *__restrict__ stamps)
+{
+    // optional phase clock of CTA 0 (MDB_SMALL_STAMPS=1, development aid): SM cycles at phase ends
+    int stamp_k = 0;
+    auto stamp = [&]() { if (stamps && blockIdx.x == 0 && threadIdx.x == 0) stamps[stamp_k++] = clock64(); };
+    stamp();
+    extern __shared__ __align__(16) unsigned char small_smem[];
+    __shared__ int warp_cnt[SMALL_WARPS];
+    __shared__ int s_raw, s_np, s_c0, s_c1;
+    __shared__ double s_thr, s_mean, s_sd;
+
+    const SmallDesc e = xd[blockIdx.x];
+    if (e.skip) return;
+    const SpecDesc d = sd[blockIdx.x];
+    const int t = threadIdx.x, lane = t & 31;
+    const int n = d.n;
+    const size_t N = (size_t)n_al;
+
+    int *sel = reinterpret_cast<int *>(small_smem);
+    double *d2 = reinterpret_cast<double *>(small_smem + 6 * N);
+    int *pk = reinterpret_cast<int *>(small_smem + 14 * N);
+    double *sc = reinterpret_cast<double *>(small_smem + 20 * N);
+    double *sfr = reinterpret_cast<double *>(small_smem + 24 * N);
+    int *cen = reinterpret_cast<int *>(small_smem + 28 * N);  // centre list, later rank / flag per centre
+    double *par_a = reinterpret_cast<double *>(small_smem + 6 * N);
+    double *par_b = reinterpret_cast<double *>(small_smem + 18 * N);
+
+    SmallOut *hdr = reinterpret_cast<SmallOut *>(e.out);
+    double *lor_out = reinterpret_cast<double *>(e.out + 64);
+    int *pk_out = reinterpret_cast<int *>(e.out + 64 + (size_t)24 * e.cap);
+
+    SmallOut o;
+    o.info.status = ST_OK; o.info.n_detected = 0; o.info.n_after_ignore = 0; o.info.n_selected = 0;
+    o.info.region_left = 0; o.info.region_right = 0; o.info.n_sfr = 0; o.info.pad_ = 0;
+    o.info.mean = 0.0; o.info.sd = 0.0;
+    o.n_kept = 0; o.pad_ = 0; o.mse = 0.0;
+
+    if (t == 0) { s_raw = 0; s_np = 0; s_c0 = 0; s_c1 = 0; }
+
+    // ---- smoothing in shared memory (smooth_iters == 0: d.ys already holds the smoothed row)
+    const double *ys = d.ys;
+    if (smooth_iters > 0) {
+        double *row0 = reinterpret_cast<double *>(small_smem + 14 * N);
+        double *row1 = reinterpret_cast<double *>(small_smem + 22 * N);
+        const double *__restrict__ y = d.y;
+        for (int j = t; j < n; j += SMALL_THREADS) row0[j] = y[j];
+        __syncthreads();
+        if (t < 32) small_smooth_warp(row0, n_al, n, smooth_iters, smooth_window);
+        __syncthreads();
+        ys = (smooth_iters & 1) ? row1 : row0;
+    }
+    stamp();  // 1: smoothed
+    // ---- second difference (common.rs:8), all of it resident
+    for (int j = t; j < n - 2; j += SMALL_THREADS) d2[j] = d2_at(ys, j);
+    __syncthreads();
+
+    // ---- centres (detector.rs:124), ascending
+    const int n_cen = small_ordered_compact(
+        2, n - 2, warp_cnt,
+        [&](int c) { const double b1 = d2[c - 1]; return b1 < 0.0 && b1 < d2[c - 2] && b1 < d2[c]; },
+        [&](int c, int rank) { cen[rank] = c; });
+    stamp();  // 2: centres
+
+    // ---- one thread per centre: borders (detector.rs:150-164), MinimumSum score (scorer.rs:65-74),
+    // first retain (noise_score_filter.rs:41-48 / detector_only.rs:26-38) and the region-split counts
+    {
+        int raw = 0, np = 0, c0 = 0, c1 = 0;
+        for (int j0 = 0; j0 < n_cen; j0 += SMALL_THREADS) {
+            const int j = j0 + t;
+            bool found = false, kept = false;
+            int c = 0;
+            if (j < n_cen) {
+                c = cen[j];
+                int ll = 0, rr = 0;
+                double pa = d2[c - 1], pb = d2[c];
+                double rsum = fabs(pa);
+                for (int q = c + 1; q <= n - 3; ++q) {
+                    const double pc = d2[q];
+                    rsum = __dadd_rn(rsum, fabs(pb));
+                    if (pb > pa && (pb >= pc || (pb < 0.0 && pc >= 0.0))) { rr = q; break; }
+                    pa = pb; pb = pc;
+                }
+                if (rr != 0) {
+                    double qc = d2[c - 1], qb = d2[c - 2];
+                    for (int q = c - 1; q >= 2; --q) {
+                        const double qa = d2[q - 2];
+                        if (qb > qc && (qb >= qa || (qb < 0.0 && qa >= 0.0))) { ll = q; break; }
+                        qc = qb; qb = qa;
+                    }
+                }
+                found = (ll != 0 && rr != 0);  // detector.rs:105
+                double score = 0.0;
+                if (found) {
+                    double lsum = 0.0;
+                    for (int u = ll - 1; u <= c - 1; ++u) lsum = __dadd_rn(lsum, fabs(d2[u]));
+                    score = fmin(lsum, rsum);
+                    kept = candidate_kept(d, selector_kind, ll, rr);
+                }
+                pk[3 * j] = ll; pk[3 * j + 1] = c; pk[3 * j + 2] = rr;
+                sc[j] = score;
+                cen[j] = found ? (kept ? 1 : 0) : -1;  // only this thread ever reads cen[j] before the barrier
+            }
+            raw += __popc(__ballot_sync(0xffffffffu, found));
+            np += __popc(__ballot_sync(0xffffffffu, kept));
+            c0 += __popc(__ballot_sync(0xffffffffu, kept && c <= d.sb0));
+            c1 += __popc(__ballot_sync(0xffffffffu, kept && c <= d.sb1));
+        }
+        if (lane == 0) {
+            if (raw) atomicAdd(&s_raw, raw);
+            if (np) atomicAdd(&s_np, np);
+            if (c0) atomicAdd(&s_c0, c0);
+            if (c1) atomicAdd(&s_c1, c1);
+        }
+    }
+    __syncthreads();
+    stamp();  // 3: borders + scores
+    const int n_raw = s_raw, np = s_np;
+    o.info.n_detected = n_raw;
+    o.info.n_after_ignore = np;
+    if (n_raw == 0) {  // detector.rs:107-109
+        if (t == 0) { o.info.status = ST_NO_PEAKS; *hdr = o; }
+        return;
+    }
+
+    int n_sel = 0;
+    if (selector_kind == 0) {  // DetectorOnly: everything that survived the retains, in order
+        n_sel = small_ordered_compact(
+            0, n_cen, warp_cnt, [&](int j) { return cen[j] == 1; },
+            [&](int j, int rank) {
+                const int l = pk[3 * j], c = pk[3 * j + 1], r = pk[3 * j + 2];
+                sel[3 * rank] = l; sel[3 * rank + 1] = c; sel[3 * rank + 2] = r;
+                pk_out[3 * rank] = l; pk_out[3 * rank + 1] = c; pk_out[3 * rank + 2] = r;
+            });
+    } else {
+        if (np == 0) {  // `peaks.len() - 1` underflows and the slicing panics (common.rs:37)
+            if (t == 0) { o.info.status = ST_PANIC; *hdr = o; }
+            return;
+        }
+        // region boundaries in the filtered list (common.rs:26-40)
+        const int cnt0 = s_c0, cnt1 = s_c1;
+        const int bl = (cnt0 < np) ? cnt0 : 0;
+        const int cand_r = (cnt1 > bl) ? cnt1 : bl;
+        const int br = (cand_r < np) ? cand_r : np - 1;
+        o.info.region_left = bl; o.info.region_right = br;
+        if (bl == 0 && br >= np) {  // noise_score_filter.rs:102-104
+            if (t == 0) { o.info.status = ST_EMPTY_SFR; *hdr = o; }
+            return;
+        }
+        if (bl == br) {             // noise_score_filter.rs:105-107
+            if (t == 0) { o.info.status = ST_EMPTY_SIGNAL; *hdr = o; }
+            return;
+        }
+        const int n_sfr = bl + (np - br);
+        o.info.n_sfr = n_sfr;
+        // ranks in the filtered list; SFR scores gathered densely: peaks[0..bl] then peaks[br..] (:109-113)
+        small_ordered_compact(
+            0, n_cen, warp_cnt, [&](int j) { return cen[j] >= 1; },
+            [&](int j, int rank) {
+                cen[j] = 2 + rank;
+                if (rank < bl) sfr[rank] = sc[j];
+                else if (rank >= br) sfr[bl + rank - br] = sc[j];
+            });
+        // ordered mean / sd (noise_score_filter.rs:129-138)
+        if (t < 32) {
+            const double total = warp_ordered_sum<0>(sfr, n_sfr, 0.0);
+            const double mean = __ddiv_rn(total, (double)n_sfr);
+            const double vs = warp_ordered_sum<1>(sfr, n_sfr, mean);
+            const double sdv = __dsqrt_rn(__ddiv_rn(vs, (double)n_sfr));
+            if (t == 0) {
+                s_mean = mean; s_sd = sdv;
+                s_thr = __dadd_rn(mean, __dmul_rn(d.threshold, sdv));  // :118, no FMA
+            }
+        }
+        __syncthreads();
+        const double thr = s_thr;
+        o.info.mean = s_mean; o.info.sd = s_sd;
+        n_sel = small_ordered_compact(
+            0, n_cen, warp_cnt,
+            [&](int j) { const int rk = cen[j] - 2; return rk >= bl && rk < br && sc[j] >= thr; },
+            [&](int j, int rank) {
+                const int l = pk[3 * j], c = pk[3 * j + 1], r = pk[3 * j + 2];
+                sel[3 * rank] = l; sel[3 * rank + 1] = c; sel[3 * rank + 2] = r;
+                pk_out[3 * rank] = l; pk_out[3 * rank + 1] = c; pk_out[3 * rank + 2] = r;
+            });
+        if (n_sel == 0) {  // :121-123
+            if (t == 0) { o.info.status = ST_EMPTY_SIGNAL; *hdr = o; }
+            return;
+        }
+    }
+    o.info.n_selected = n_sel;
+    stamp();  // 4: selected
+    // (the compaction ended with a barrier: d2 / pk / sc / sfr / cen are dead from here on)
+
+    // ---- fit (fitter_analytical.rs:19-72).  Parameters ping-pong in shared memory; per-peak stencil
+    // state and the 3P superposition values live in the CTA's scratch rows (fit_state, 14 x cap).
+    // A refinement pass has two steps: one thread per (stencil point, peak) evaluates the ordered
+    // superposition there (3P independent chains instead of P), then one thread per peak forms the
+    // ratios, mirrors and re-solves.
+    const int P = n_sel;
+    const size_t cap = (size_t)e.cap;
+    double *ox = e.fit_state, *oy = ox + 3 * cap;           // original stencils: [point][peak]
+    double *sx1 = oy + 3 * cap, *sx3 = sx1 + cap;           // current stencil x (x2 never changes)
+    double *sy = sx3 + cap;                                 // current stencil y: [point][peak]
+    double *sup = sy + 3 * cap;                             // superposition at the original x: [point][peak]
+    bool ok = true;   // this thread's positions / parameters are inside div_fast's domain
+    bool pok = true;
+    for (int k = t; k < P; k += SMALL_THREADS) {
+        const int l = sel[3 * k], c = sel[3 * k + 1], r = sel[3 * k + 2];
+        Stencil p;
+        p.x1 = d.x[l]; p.x2 = d.x[c]; p.x3 = d.x[r];
+        p.y1 = d.y[l]; p.y2 = d.y[c]; p.y3 = d.y[r];
+        ox[k] = p.x1; ox[cap + k] = p.x2; ox[2 * cap + k] = p.x3;
+        oy[k] = p.y1; oy[cap + k] = p.y2; oy[2 * cap + k] = p.y3;
+        ok = ok && x_fast_domain(p.x1) && x_fast_domain(p.x2) && x_fast_domain(p.x3);
+        mirror_shoulder(p);
+        sx1[k] = p.x1; sx3[k] = p.x3;
+        sy[k] = p.y1; sy[cap + k] = p.y2; sy[2 * cap + k] = p.y3;
+        double sfhw, hw2, maxp;
+        solve_stencil(p, sfhw, hw2, maxp);
+        par_a[3 * k] = sfhw; par_a[3 * k + 1] = hw2; par_a[3 * k + 2] = maxp;
+        pok = pok && params_fast_domain(sfhw, hw2, maxp);
+    }
+    stamp();  // 5: stencils + first solve
+    const bool x_ok = __syncthreads_and(ok);  // positions never change; parameters are re-checked every pass
+    bool fast = __syncthreads_and(pok) && x_ok;
+    for (int it = 0; it < e.n_iters; ++it) {
+        const double *pin = (it & 1) ? par_b : par_a;
+        double *pout = (it & 1) ? par_a : par_b;
+        for (int w = t; w < 3 * P; w += SMALL_THREADS) {
+            const int q = w / P, k = w - q * P;
+            const double x = ox[q * cap + k];
+            double acc = 0.0;
+            if (fast) {
+                int j = 0;
+                for (; j + 8 <= P; j += 8) lorentz_multi<8>(pin + 3 * j, x, acc);
+                if (j + 4 <= P) { lorentz_multi<4>(pin + 3 * j, x, acc); j += 4; }
+                if (j + 2 <= P) { lorentz_multi<2>(pin + 3 * j, x, acc); j += 2; }
+                if (j < P) lorentz_multi<1>(pin + 3 * j, x, acc);
+            } else {
+                const double xs[1] = {x};
+                double as[1] = {0.0};
+#pragma unroll 1
+                for (int j = 0; j < P; ++j) lorentz_step<1, false>(pin[3 * j], pin[3 * j + 1], pin[3 * j + 2], xs, as);
+                acc = as[0];
+            }
+            sup[q * cap + k] = acc;
+        }
+        __syncthreads();
+        pok = true;
+        for (int k = t; k < P; k += SMALL_THREADS) {
+            Stencil p;
+            p.x1 = sx1[k]; p.x2 = ox[cap + k]; p.x3 = sx3[k];
+            p.y1 = __dmul_rn(sy[k], __ddiv_rn(oy[k], sup[k]));  // :42-54
+            p.y2 = __dmul_rn(sy[cap + k], __ddiv_rn(oy[cap + k], sup[cap + k]));
+            p.y3 = __dmul_rn(sy[2 * cap + k], __ddiv_rn(oy[2 * cap + k], sup[2 * cap + k]));
+            mirror_shoulder(p);
+            sx1[k] = p.x1; sx3[k] = p.x3;
+            sy[k] = p.y1; sy[cap + k] = p.y2; sy[2 * cap + k] = p.y3;
+            double sfhw, hw2, maxp;
+            solve_stencil(p, sfhw, hw2, maxp);
+            pout[3 * k] = sfhw; pout[3 * k + 1] = hw2; pout[3 * k + 2] = maxp;
+            pok = pok && params_fast_domain(sfhw, hw2, maxp);
+        }
+        fast = __syncthreads_and(pok) && x_ok;
+    }
+
+    stamp();  // 6: refinement passes
+    // ---- retain (fitter_analytical.rs:67-69): compact into the other buffer and into the result slot
+    const double *__restrict__ fin = (e.n_iters & 1) ? par_b : par_a;
+    double *__restrict__ kept = (e.n_iters & 1) ? par_a : par_b;
+    double *__restrict__ resid = (e.n_iters & 1) ? par_b : par_a;  // overlays `fin` once the compaction is done
+    const double CP = 1.0e+3 * 2.220446049250313e-16;  // lib.rs:277
+    const int n_kept = small_ordered_compact(
+        0, P, warp_cnt, [&](int k) { return fin[3 * k] > CP && fin[3 * k + 1] > CP; },
+        [&](int k, int rank) {
+            const double a = fin[3 * k], h = fin[3 * k + 1], m = fin[3 * k + 2];
+            kept[3 * rank] = a; kept[3 * rank + 1] = h; kept[3 * rank + 2] = m;
+            lor_out[3 * rank] = a; lor_out[3 * rank + 1] = h; lor_out[3 * rank + 2] = m;
+        });
+    o.n_kept = n_kept;
+
+    // ---- MSE (deconvoluter.rs:828-862): superposition of the kept Lorentzians on every range point
+    bool kok = true;
+    for (int k = t; k < n_kept; k += SMALL_THREADS) kok = kok && params_fast_domain(kept[3 * k], kept[3 * k + 1], kept[3 * k + 2]);
+    const bool kfast = __syncthreads_and(kok);
+    {
+        int pos = 0;
+        for (int q = 0; q < e.n_ranges; ++q) {
+            const int s0 = e.ranges[2 * q], e0 = e.ranges[2 * q + 1];
+            for (int i0 = s0; i0 < e0; i0 += SMALL_THREADS * SMALL_R) {
+                double xv[SMALL_R], acc[SMALL_R];
+                int idx[SMALL_R];
+                bool xok = true;
+#pragma unroll
+                for (int r = 0; r < SMALL_R; ++r) {
+                    idx[r] = i0 + t + r * SMALL_THREADS;
+                    xv[r] = (idx[r] < e0) ? d.x[idx[r]] : 0.0;
+                    acc[r] = 0.0;
+                    xok = xok && x_fast_domain(xv[r]);
+                }
+                if (idx[0] < e0) {
+                    if (kfast && xok) {
+#pragma unroll 2
+                        for (int j = 0; j < n_kept; ++j) lorentz_step<SMALL_R, true>(kept[3 * j], kept[3 * j + 1], kept[3 * j + 2], xv, acc);
+                    } else {
+#pragma unroll 1
+                        for (int j = 0; j < n_kept; ++j) lorentz_step<SMALL_R, false>(kept[3 * j], kept[3 * j + 1], kept[3 * j + 2], xv, acc);
+                    }
+#pragma unroll
+                    for (int r = 0; r < SMALL_R; ++r)
+                        if (idx[r] < e0) {
+                            const double dd = __dsub_rn(acc[r], d.y[idx[r]]);  // :852
+                            resid[pos + idx[r] - s0] = __dmul_rn(dd, dd);
+                        }
+                }
+            }
+            pos += e0 - s0;
+        }
+    }
+    __syncthreads();
+    stamp();  // 7: MSE superposition
+    if (t == 0) {
+        // each range is a left fold from 0.0, the range sums are folded in range order (:846-861)
+        double residuals = 0.0;
+        long long length = 0;
+        int pos = 0;
+        for (int q = 0; q < e.n_ranges; ++q) {
+            const int len = e.ranges[2 * q + 1] - e.ranges[2 * q];
+            const double *__restrict__ src = resid + pos;
+            double part = 0.0;
+            int i = 0;
+            for (; i + 8 <= len; i += 8) {
+                const double r0 = src[i], r1 = src[i + 1], r2 = src[i + 2], r3 = src[i + 3];
+                const double r4 = src[i + 4], r5 = src[i + 5], r6 = src[i + 6], r7 = src[i + 7];
+                part = __dadd_rn(part, r0); part = __dadd_rn(part, r1);
+                part = __dadd_rn(part, r2); part = __dadd_rn(part, r3);
+                part = __dadd_rn(part, r4); part = __dadd_rn(part, r5);
+                part = __dadd_rn(part, r6); part = __dadd_rn(part, r7);
+            }
+            for (; i < len; ++i) part = __dadd_rn(part, src[i]);
+            residuals = __dadd_rn(residuals, part);
+            length += len;
+            pos += len;
+        }
+        o.mse = __ddiv_rn(residuals, (double)length);
+        *hdr = o;
+    }
+    stamp();  // 8: ordered fold, header written
+}
+
+}  // namespace mdb

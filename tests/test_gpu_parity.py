@@ -850,6 +850,167 @@ def test_randomised_differential_gpu_vs_oracle():
         done += batch
 
 
+# ------------------------------------------------------------------------------ small-spectrum path
+def _launches_of(fn):
+    lib = _lib.load()
+    lib.mdb_reset_kernel_launch_count()
+    out = fn()
+    return out, int(lib.mdb_kernel_launch_count())
+
+
+def _same_results(a, b, what):
+    assert len(a) == len(b)
+    for i, (u, v) in enumerate(zip(a, b)):
+        assert np.array_equal(u.peaks, v.peaks), f"{what}[{i}]: peaks"
+        assert np.array_equal(bits(u.parameters), bits(v.parameters)), f"{what}[{i}]: lorentzians"
+        assert bits([u.mse])[0] == bits([v.mse])[0], f"{what}[{i}]: mse"
+
+
+def test_small_path_is_one_launch_and_matches_general_path_and_oracle(monkeypatch, golden_dir):
+    """Spectra of <= 4 096 points run as ONE fused launch (small_fused.cuh), smoothing included; the
+    same kernel behind the batch smoothing kernel (MDB_SMALL_SMOOTH=separate), the general chunk
+    pipeline (MDB_SMALL_PATH=0) and the oracle must all give the same bits."""
+    sim = Spectrum.read_bruker(os.path.join(golden_dir, "bruker", "sim_01"), 10, 10, (3.35, 3.55))
+    dec = Deconvoluter()
+    small, launches = _launches_of(lambda: _check_e2e(dec, O.Settings(), [sim], "sim_01 small path"))
+    assert launches == 1, launches
+    monkeypatch.setenv("MDB_SMALL_SMOOTH", "separate")
+    two, launches_two = _launches_of(lambda: dec.deconvolute_spectra([sim]))
+    monkeypatch.delenv("MDB_SMALL_SMOOTH")
+    assert launches_two == 2, launches_two
+    _same_results(small, two, "sim_01, smoothing as its own launch")
+    monkeypatch.setenv("MDB_SMALL_PATH", "0")
+    general, launches_general = _launches_of(lambda: dec.deconvolute_spectra([sim]))
+    monkeypatch.delenv("MDB_SMALL_PATH")
+    assert launches_general > 10
+    _same_results(small, general, "sim_01")
+    # a batch: mixed lengths up to the limit, integer and float values, every spectrum its own axis object
+    specs = []
+    for s, n in enumerate([4096, 2048, 4095, 517, 64, 3000, 4096, 1025]):
+        x = synth.axis(n)
+        specs.append(Spectrum(x, synth.spectrum(300 + s, n=n, k=max(3, n // 60), hw_range=(8e-3, 5e-2), integer=bool(s & 1), x=x),
+                              (-2.2, 11.8)))
+    for setup, settings in [
+        (lambda d: None, O.Settings()),
+        (lambda d: (d.set_moving_average_smoother(4, 5), d.set_noise_score_selector(2.5), d.set_analytical_fitter(3),
+                    d.add_ignore_region((4.7, 4.9))),
+         O.Settings(smoothing_iterations=4, smoothing_window=5, threshold=2.5, fitting_iterations=3, ignore_regions=[(4.7, 4.9)])),
+        (lambda d: (d.set_identity_smoother(), d.set_noise_score_selector(3.0)),
+         O.Settings(smoothing_kind=O.SMOOTH_IDENTITY, threshold=3.0)),
+        (lambda d: (d.set_detector_only(), d.set_analytical_fitter(2)),
+         O.Settings(selection_kind=O.SELECT_DETECTOR_ONLY, fitting_iterations=2)),
+        (lambda d: (d.set_moving_average_smoother(2, 11), d.set_noise_score_selector(1.0)),
+         O.Settings(smoothing_iterations=2, smoothing_window=11, threshold=1.0)),
+        (lambda d: (d.set_moving_average_smoother(7, 2), d.set_noise_score_selector(1.5)),
+         O.Settings(smoothing_iterations=7, smoothing_window=2, threshold=1.5)),
+        (lambda d: (d.set_moving_average_smoother(1, 40), d.set_noise_score_selector(1.5)),
+         O.Settings(smoothing_iterations=1, smoothing_window=40, threshold=1.5)),
+        (lambda d: (d.set_moving_average_smoother(33, 3), d.set_noise_score_selector(1.5)),  # > 32 passes: smoothing launched separately
+         O.Settings(smoothing_iterations=33, smoothing_window=3, threshold=1.5)),
+    ]:
+        dec = Deconvoluter()
+        setup(dec)
+        ok = [sp for sp in specs
+              if O.deconvolute_spectrum(settings, sp.chemical_shifts, sp.intensities, sp.signal_boundaries).status == O.OK]
+        assert len(ok) >= 4
+        small, launches = _launches_of(lambda: _check_e2e(dec, settings, ok, "small batch"))
+        assert launches == (1 if settings.smoothing_iterations <= 32 else 34), launches
+        monkeypatch.setenv("MDB_SMALL_PATH", "0")
+        general = dec.deconvolute_spectra(ok)
+        monkeypatch.delenv("MDB_SMALL_PATH")
+        _same_results(small, general, "small batch vs general")
+
+
+def test_small_path_dense_peaks_short_inputs_and_errors():
+    """Worst-case peak density (a centre every other point fills the per-centre arrays), more
+    selected peaks than the CTA has threads, the shortest inputs, and every error status."""
+    rng = np.random.default_rng(4096)
+    # zig-zag: the second difference alternates in sign, so every other interior point is a centre
+    n = 4096
+    x = synth.axis(n)
+    zig = 1000.0 + 50.0 * (np.arange(n) % 2) + rng.uniform(0.0, 5.0, n) + 4000.0 / (1.0 + ((x - 5.0) / 0.5) ** 2)
+    sp = Spectrum(x, zig, (-2.2, 11.8))
+    dec = Deconvoluter()
+    dec.set_identity_smoother()
+    dec.set_detector_only()
+    dec.set_analytical_fitter(3)
+    settings = O.Settings(smoothing_kind=O.SMOOTH_IDENTITY, selection_kind=O.SELECT_DETECTOR_ONLY, fitting_iterations=3)
+    r = O.deconvolute_spectrum(settings, x, zig, sp.signal_boundaries)
+    assert r.status == O.OK and len(r.peaks) > 1200, len(r.peaks)   # > 256 peaks: several peaks per thread
+    _check_e2e(dec, settings, [sp], "zig-zag, detector only")
+    dec = Deconvoluter()
+    dec.set_identity_smoother()
+    dec.set_noise_score_selector(0.1)
+    settings = O.Settings(smoothing_kind=O.SMOOTH_IDENTITY, threshold=0.1)
+    r = O.deconvolute_spectrum(settings, x, zig, sp.signal_boundaries)
+    assert r.status == O.OK and len(r.peaks) > 256, len(r.peaks)
+    _check_e2e(dec, settings, [sp], "zig-zag, noise score filter")
+    # shortest inputs the API accepts, default and loose settings: statuses must agree with the oracle
+    from metabodecon_rust_b200 import exceptions as E
+    status_to_exc = {O.NO_PEAKS_DETECTED: E.NoPeaksDetected, O.EMPTY_SIGNAL_REGION: E.EmptySignalRegion,
+                     O.EMPTY_SIGNAL_FREE_REGION: E.EmptySignalFreeRegion, O.PANIC: E.UnexpectedError}
+    seen = set()
+    for n in list(range(5, 40)) + [63, 64, 65, 255, 256, 257]:
+        for trial in range(4):
+            xs = 10.0 - np.arange(n) * (10.0 / (n - 1))
+            y = np.rint(rng.normal(0.0, 100.0, n)) if trial & 1 else rng.normal(0.0, 100.0, n)
+            lo, hi = sorted(rng.uniform(0.5, 9.5, 2))
+            sp = Spectrum(xs, y, (lo, hi))
+            for thr in (0.01, 5.0):
+                dec = Deconvoluter()
+                dec.set_moving_average_smoother(1, 3)
+                dec.set_noise_score_selector(thr)
+                settings = O.Settings(smoothing_iterations=1, smoothing_window=3, threshold=thr)
+                r = O.deconvolute_spectrum(settings, xs, y, sp.signal_boundaries)
+                seen.add(r.status)
+                if r.status == O.OK:
+                    _check_e2e(dec, settings, [sp], f"n={n}")
+                else:
+                    with pytest.raises(status_to_exc[r.status]):
+                        dec.deconvolute_spectrum(sp)
+    assert O.OK in seen and len(seen) >= 3, seen
+
+
+def test_small_path_many_spectra_device_memory_and_chunking():
+    """2 000 small spectra in one call (several fused launches: the result slots are capped at
+    64 MiB per chunk), from host memory and from device memory; results must not depend on either."""
+    torch = pytest.importorskip("torch")
+    lib = _lib.load()
+    n = 4096
+    x = synth.axis(n)
+    base = [synth.spectrum(500 + s, n=n, k=40, hw_range=(8e-3, 5e-2), x=x) for s in range(8)]
+    want = [O.deconvolute_spectrum(O.Settings(), x, y, synth.SIGNAL_BOUNDARIES) for y in base]
+    assert all(w.status == O.OK for w in want)
+    total = 2000
+    specs = [Spectrum(x, base[s % 8], (-2.2, 11.8)) for s in range(total)]
+    dec = Deconvoluter()
+    outs, launches = _launches_of(lambda: dec.deconvolute_spectra(specs))
+    assert launches == 3, launches   # 909 result slots of 73 792 bytes fit in 64 MiB -> chunks of 909, 909, 182
+    for s in range(total):
+        w = want[s % 8]
+        assert np.array_equal(outs[s].peaks.astype(np.int64), w.peaks.astype(np.int64)), s
+        assert np.array_equal(bits(outs[s].parameters), bits(w.lorentzians)), s
+        assert outs[s].mse == w.mse, s
+    xd = torch.from_numpy(x).cuda()
+    yd = torch.from_numpy(np.stack(base)).cuda()
+    views = (_lib.SpectrumView * 8)()
+    for i in range(8):
+        views[i].chemical_shifts = xd.data_ptr()
+        views[i].intensities = yd[i].data_ptr()
+        views[i].len = n
+        views[i].signal_boundaries[0], views[i].signal_boundaries[1] = 11.8, -2.2
+    batch = C.c_void_p()
+    assert lib.mdb_deconvolute_spectra(dec._h, views, 8, _lib.MDB_MEM_DEVICE, C.byref(batch)) == 0, _lib.last_error()
+    try:
+        for i in range(8):
+            k = lib.mdb_batch_n_lorentzians(batch, i)
+            got = np.ctypeslib.as_array(C.cast(lib.mdb_batch_lorentzians(batch, i), C.POINTER(C.c_double)), (k, 3)).copy()
+            assert np.array_equal(bits(got), bits(want[i].lorentzians)), i
+            assert lib.mdb_batch_mse(batch, i) == want[i].mse
+    finally:
+        lib.mdb_batch_free(batch)
+
+
 # ------------------------------------------------------------------------------ re-entrancy
 def test_concurrent_callers_share_one_deconvoluter():
     """The reference's Deconvoluter is Send + Sync (deconvoluter.rs:913-917) and rayon calls it from

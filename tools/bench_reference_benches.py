@@ -58,3 +58,20 @@ for name, gpu, cpu, threads in rows:
     c_min, c_med = best_of(cpu, 3)
     print(json.dumps({"bench": name, "gpu_ms_median": g_med * 1e3, "gpu_ms_min": g_min * 1e3, "oracle_ms_median": c_med * 1e3,
                       "oracle_threads": threads, "speedup_median": c_med / g_med}), flush=True)
+
+# where a single small spectrum spends its time on the device (CUDA events inside the library)
+import ctypes as C  # noqa: E402
+from metabodecon_rust_b200 import _lib  # noqa: E402
+lib = _lib.load()
+lib.mdb_profile_enable(1)
+lib.mdb_profile_reset()
+for _ in range(20):
+    dec.deconvolute_spectrum(sim)
+prof = {}
+for kid, name in enumerate(_lib.KERNEL_NAMES):
+    ms, n, work = C.c_double(), C.c_uint64(), C.c_double()
+    lib.mdb_profile_read(kid, C.byref(ms), C.byref(n), C.byref(work))
+    if n.value:
+        prof[name] = {"us_per_launch": 1e3 * ms.value / n.value, "launches": int(n.value)}
+lib.mdb_profile_enable(0)
+print(json.dumps({"bench": "sim_spectrum_device_time", "kernels": prof}), flush=True)
