@@ -92,6 +92,17 @@ __device__ __forceinline__ int small_ordered_compact(int begin, int end, int *wa
     return tot;
 }
 
+__device__ __forceinline__ double lds_f64(uint32_t a)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f64(uint32_t a, double v)
+{
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+}
+
 // U consecutive Lorentzians (AoS triples at p) at ONE point, fast-domain division: the U
 // quotients are independent and interleave stage by stage (what lorentz_step does across points),
 // then join the running sum in index order -- the same operations per element as lorentz_step.
@@ -127,61 +138,93 @@ __device__ __forceinline__ void lorentz_multi(const double *p, const double x, d
     for (int u = 0; u < U; ++u) acc = __dadd_rn(acc, q[u]);
 }
 
+// Squared residuals of R points per thread, points i0 + t + r * SMALL_THREADS below e0
+// (deconvoluter.rs:846-855): ordered superposition of the kept Lorentzians, minus y, squared.
+template <int R>
+__device__ __forceinline__ void small_mse_block(const double *__restrict__ x, const double *__restrict__ y, const double *kept,
+                                                int n_kept, bool kfast, int i0, int e0, double *resid)
+{
+    double xv[R], acc[R];
+    int idx[R];
+    bool xok = true;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        idx[r] = i0 + (int)threadIdx.x + r * SMALL_THREADS;
+        xv[r] = (idx[r] < e0) ? x[idx[r]] : 0.0;
+        acc[r] = 0.0;
+        xok = xok && x_fast_domain(xv[r]);
+    }
+    if (idx[0] >= e0) return;
+    if (kfast && xok) {
+#pragma unroll 2
+        for (int j = 0; j < n_kept; ++j) lorentz_step<R, true>(kept[3 * j], kept[3 * j + 1], kept[3 * j + 2], xv, acc);
+    } else {
+#pragma unroll 1
+        for (int j = 0; j < n_kept; ++j) lorentz_step<R, false>(kept[3 * j], kept[3 * j + 1], kept[3 * j + 2], xv, acc);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+        if (idx[r] < e0) {
+            const double dd = __dsub_rn(acc[r], y[idx[r]]);  // :852
+            resid[idx[r]] = __dmul_rn(dd, dd);
+        }
+}
+
 // Moving average of one spectrum by ONE warp (smoothing/moving_average.rs:53-83, the recurrence of
-// smooth_pass_generic_kernel): lane p runs pass p, Db blocks of SMALL_SMOOTH_U points behind lane
-// p-1, reading that lane's output row and writing the other row (pass p reads row p&1).  Every
-// pass is still the reference's sequential running sum -- two dependent additions per point -- but
-// the passes overlap, and a block's loads are issued together ahead of its chain.
-// Hazards: a lane reads indices up to i0+U-1+r, written by its producer at least
-// one iteration earlier when Db >= 2 + (r-1)/U; the lane behind it overwrites indices below
-// (mb-Db+1)U of the row this lane reads, which it no longer needs when (Db-1)U >= W-r.
-constexpr int SMALL_SMOOTH_U = 16;
+// smooth_pass_generic_kernel): lane p runs pass p, `db` blocks of U points behind lane p-1, reading
+// the row that lane writes and writing the other row (pass p reads row p&1).  Every pass is still
+// the reference's sequential running sum -- two dependent additions per point, 16.4 cycles -- but
+// the passes overlap.  A single warp has nobody to hide behind, so everything that is not on the
+// chain is kept out of its way:
+//  * one code shape for every block.  A step is always `sum = sum + a; sum = sum - q; out = sum * div`
+//    with a = in[i+r] or -0.0 when the window has run off the end (x + -0.0 == x for every x) and
+//    q = in[i+r-w] or +0.0 while the window is still filling (x - 0.0 == x for every x), so the
+//    edges cost a few predicated loads and divisions instead of a branchy per-point loop;
+//  * interior blocks run in a lean loop: no edge tests, the inputs of block mb+1 are fetched into a
+//    second register set while the chain of block mb runs (two rounds per iteration, sets swapped);
+//  * lanes without a pass shadow lane 0 (stores to a sink), so the warp stays converged and the
+//    per-round __syncwarp() is its cheap converged form;
+//  * shared memory is addressed through 32-bit shared-space addresses held in registers (left to
+//    itself the compiler re-derives the window base, S2UR SR_CgaCtaId, inside the loop and the
+//    in-order warp waits for it).
+// `div` follows the reference: recomputed as 1/len only in steps where the window grows or
+// shrinks, carried otherwise.  Inputs shorter than the window (n < w) take the per-point form.
+// Hazards: with the prefetch a lane reads, in round b, indices up to (mb+2)U-1+r of its input row,
+// all written by its producer before round b when db >= 3 + (r-1)/U, and none written in round b
+// itself; the lane behind it overwrites indices below (mb-db+1)U of that row, which this lane no
+// longer reads when db*U >= w-r.  db = 2 + ceil(max(r, w-r)/U) satisfies both.
+constexpr int SMALL_SMOOTH_U = 8;
 constexpr int SMALL_SMOOTH_MAX_ITERS = 32;
 
-__device__ __forceinline__ void small_smooth_warp(double *rows, int row_stride, int n, int iters, int w)
+__device__ __forceinline__ void small_smooth_warp(double *rows, int row_stride, int n, int iters, int w, double *sink)
 {
     constexpr int U = SMALL_SMOOTH_U;
     const int lane = threadIdx.x & 31;
     const int r = w / 2;
-    const int db = 1 + (max(r, w - r) + U - 1) / U;
+    const int db = 2 + (max(r, w - r) + U - 1) / U;
     const int n_blocks = (n + U - 1) / U;
-    const bool active = lane < iters;
-    // pass p reads row p&1 and writes the other one; plain indices into one array (no __restrict__:
-    // other lanes write what this one reads)
+    // pass p reads row p&1 and writes the other one
     const int in_o = (lane & 1) * row_stride, out_o = row_stride - in_o;
     double sum = 0.0, div = 1.0;
-    int len = 0;
     const int rounds = n_blocks + (iters - 1) * db;
-    for (int b = 0; b < rounds; ++b) {
-        const int mb = b - lane * db;
-        if (active && mb >= 0 && mb < n_blocks) {
-            const int i0 = mb * U;
-            if (mb == 0) {
-                for (int k = 0; k < r && k < n; ++k) sum = __dadd_rn(sum, rows[in_o + k]);
-                len = n < w ? n : w;
-            }
-            if (i0 >= w - r && i0 + U <= n - r) {  // window full, no edge in this block
-                double a[U], q[U];
-                const double *pa = rows + in_o + i0 + r, *pq = pa - w;
-#pragma unroll
-                for (int u = 0; u < U; ++u) { a[u] = pa[u]; q[u] = pq[u]; }
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    sum = __dadd_rn(sum, a[u]);
-                    sum = __dsub_rn(sum, q[u]);
-                    a[u] = __dmul_rn(sum, div);
+
+    if (n < w) {  // the window never fills: per-point form, as smooth_pass_generic_kernel
+        if (lane >= iters) return;  // the caller's CTA barrier collects the other lanes
+        const unsigned mask = iters >= 32 ? 0xffffffffu : ((1u << iters) - 1u);
+        int len = 0;
+        for (int b = 0; b < rounds; ++b) {
+            const int mb = b - lane * db;
+            if (mb >= 0 && mb < n_blocks) {
+                if (mb == 0) {
+                    for (int k = 0; k < r && k < n; ++k) sum = __dadd_rn(sum, rows[in_o + k]);
+                    len = n;
                 }
-                double *po = rows + out_o + i0;
-#pragma unroll
-                for (int u = 0; u < U; ++u) po[u] = a[u];
-            } else {
                 for (int u = 0; u < U; ++u) {
-                    const int i = i0 + u;
+                    const int i = mb * U + u;
                     if (i >= n) break;
                     if (i < n - r) {
                         sum = __dadd_rn(sum, rows[in_o + i + r]);
-                        if (i + r >= w) sum = __dsub_rn(sum, rows[in_o + i + r - w]);
-                        else div = __ddiv_rn(1.0, (double)(i + r + 1));
+                        div = __ddiv_rn(1.0, (double)(i + r + 1));
                         rows[out_o + i] = __dmul_rn(sum, div);
                     } else if (len > 0) {
                         sum = __dsub_rn(sum, rows[in_o + n - len]);
@@ -191,9 +234,96 @@ __device__ __forceinline__ void small_smooth_warp(double *rows, int row_stride, 
                     }
                 }
             }
+            __syncwarp(mask);
+        }
+        return;
+    }
+
+    // Lanes without a pass run along as ghosts of lane 0 (same reads, stores dropped or sent to a
+    // sink), so the warp never diverges for long and the per-round barrier is the converged
+    // __syncwarp() fast path instead of a masked one (MATCH / REDUX / VOTE every round).
+    const bool ghost = lane >= iters;
+    const uint32_t rows_s = smem_addr(rows);
+    uint32_t in_s = rows_s + (ghost ? 0u : 8u * (uint32_t)in_o), out_s = rows_s + 8u * (uint32_t)out_o;
+    int blk0 = ghost ? 0 : -lane * db;  // this lane's block in round b is b + blk0
+    asm volatile("" : "+r"(in_s), "+r"(out_s), "+r"(blk0));  // opaque: held in registers, never re-derived
+
+    // any block, edges included (n >= w)
+    auto edge_round = [&](int b) {
+        const int mb = b + blk0;
+        if (mb >= 0 && mb < n_blocks) {
+            const int i0 = mb * U;
+            if (mb == 0)
+                for (int k = 0; k < r; ++k) sum = __dadd_rn(sum, lds_f64(in_s + 8u * k));
+            double a[U], q[U], dv[U];
+            bool redo[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int ai = i0 + u + r, qi = ai - w;
+                a[u] = (ai < n) ? lds_f64(in_s + 8u * ai) : -0.0;
+                q[u] = (qi >= 0) ? lds_f64(in_s + 8u * qi) : 0.0;
+                redo[u] = qi < 0 || ai >= n;  // the window grows or shrinks in this step
+                dv[u] = redo[u] ? __ddiv_rn(1.0, (double)(min(ai, n - 1) - max(qi, -1))) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                sum = __dadd_rn(sum, a[u]);
+                sum = __dsub_rn(sum, q[u]);
+                if (redo[u]) div = dv[u];
+                a[u] = __dmul_rn(sum, div);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (i0 + u < n && !ghost) sts_f64(out_s + 8u * (i0 + u), a[u]);
         }
         __syncwarp();
+    };
+    // one interior round: chain over the block held in (ca, cq), next block fetched into (na, nq);
+    // pa_s: address of this lane's in[i0 + r], po_s: of its out[i0]
+    uint32_t pa_s = 0, po_s = 0;
+    const uint32_t w8 = 8u * (uint32_t)w, po_step = ghost ? 0u : 8u * U;
+    auto lean_round = [&](double (&ca)[U], double (&cq)[U], double (&na)[U], double (&nq)[U], bool prefetch) {
+        if (prefetch) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) { na[u] = lds_f64(pa_s + 8u * (U + u)); nq[u] = lds_f64(pa_s + 8u * (U + u) - w8); }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            sum = __dadd_rn(sum, ca[u]);
+            sum = __dsub_rn(sum, cq[u]);
+            ca[u] = __dmul_rn(sum, div);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) sts_f64(po_s + 8u * u, ca[u]);
+        pa_s += 8u * U;
+        po_s += po_step;
+        __syncwarp();
+    };
+
+    // interior blocks: window full (i0 >= w - r) and no tail (i0 + U <= n - r)
+    const int f0 = (w - r + U - 1) / U, f1 = (n - r) / U - 1;
+    const int b_lo = f0 + (iters - 1) * db, b_hi = f1;  // rounds in which EVERY pass is on an interior block
+    int b = 0;
+    if (b_hi - b_lo >= 3) {
+        for (; b < b_lo; ++b) edge_round(b);
+        double a0[U], q0[U], a1[U], q1[U];
+        {
+            const int i0 = (b + blk0) * U;
+            pa_s = in_s + 8u * (uint32_t)(i0 + r);
+            po_s = ghost ? smem_addr(sink) : out_s + 8u * (uint32_t)i0;
+            asm volatile("" : "+r"(pa_s), "+r"(po_s));
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) { a0[u] = lds_f64(pa_s + 8u * u); q0[u] = lds_f64(pa_s + 8u * u - w8); }
+        int left = b_hi - b + 1;  // interior rounds to go
+        b = b_hi + 1;
+        for (; left >= 2; left -= 2) {
+            lean_round(a0, q0, a1, q1, true);
+            lean_round(a1, q1, a0, q0, left > 2);
+        }
+        if (left == 1) lean_round(a0, q0, a1, q1, false);
     }
+    for (; b < rounds; ++b) edge_round(b);
 }
 
 __global__ void __launch_bounds__(SMALL_THREADS)
@@ -206,6 +336,7 @@ small_fused_kernel(const SpecDesc *__restrict__ sd, const SmallDesc *__restrict_
     stamp();
     extern __shared__ __align__(16) unsigned char small_smem[];
     __shared__ int warp_cnt[SMALL_WARPS];
+    __shared__ __align__(16) double smooth_sink[SMALL_SMOOTH_U];
     __shared__ int s_raw, s_np, s_c0, s_c1;
     __shared__ double s_thr, s_mean, s_sd;
 
@@ -245,7 +376,7 @@ small_fused_kernel(const SpecDesc *__restrict__ sd, const SmallDesc *__restrict_
         const double *__restrict__ y = d.y;
         for (int j = t; j < n; j += SMALL_THREADS) row0[j] = y[j];
         __syncthreads();
-        if (t < 32) small_smooth_warp(row0, n_al, n, smooth_iters, smooth_window);
+        if (t < 32) small_smooth_warp(row0, n_al, n, smooth_iters, smooth_window, smooth_sink);
         __syncthreads();
         ys = (smooth_iters & 1) ? row1 : row0;
     }
@@ -401,7 +532,7 @@ small_fused_kernel(const SpecDesc *__restrict__ sd, const SmallDesc *__restrict_
     double *ox = e.fit_state, *oy = ox + 3 * cap;           // original stencils: [point][peak]
     double *sx1 = oy + 3 * cap, *sx3 = sx1 + cap;           // current stencil x (x2 never changes)
     double *sy = sx3 + cap;                                 // current stencil y: [point][peak]
-    double *sup = sy + 3 * cap;                             // superposition at the original x: [point][peak]
+    double *sup = sy + 3 * cap;                             // rescaled stencil y of the running pass: [point][peak]
     bool ok = true;   // this thread's positions / parameters are inside div_fast's domain
     bool pok = true;
     for (int k = t; k < P; k += SMALL_THREADS) {
@@ -443,16 +574,15 @@ small_fused_kernel(const SpecDesc *__restrict__ sd, const SmallDesc *__restrict_
                 for (int j = 0; j < P; ++j) lorentz_step<1, false>(pin[3 * j], pin[3 * j + 1], pin[3 * j + 2], xs, as);
                 acc = as[0];
             }
-            sup[q * cap + k] = acc;
+            // ratio = y_orig / superposition (:42-47), y_k = y_k * ratio_k (:52-54), here where 3P threads share the divisions
+            sup[q * cap + k] = __dmul_rn(sy[q * cap + k], __ddiv_rn(oy[q * cap + k], acc));
         }
         __syncthreads();
         pok = true;
         for (int k = t; k < P; k += SMALL_THREADS) {
             Stencil p;
             p.x1 = sx1[k]; p.x2 = ox[cap + k]; p.x3 = sx3[k];
-            p.y1 = __dmul_rn(sy[k], __ddiv_rn(oy[k], sup[k]));  // :42-54
-            p.y2 = __dmul_rn(sy[cap + k], __ddiv_rn(oy[cap + k], sup[cap + k]));
-            p.y3 = __dmul_rn(sy[2 * cap + k], __ddiv_rn(oy[2 * cap + k], sup[2 * cap + k]));
+            p.y1 = sup[k]; p.y2 = sup[cap + k]; p.y3 = sup[2 * cap + k];
             mirror_shoulder(p);
             sx1[k] = p.x1; sx3[k] = p.x3;
             sy[k] = p.y1; sy[cap + k] = p.y2; sy[2 * cap + k] = p.y3;
@@ -487,33 +617,15 @@ small_fused_kernel(const SpecDesc *__restrict__ sd, const SmallDesc *__restrict_
         int pos = 0;
         for (int q = 0; q < e.n_ranges; ++q) {
             const int s0 = e.ranges[2 * q], e0 = e.ranges[2 * q + 1];
-            for (int i0 = s0; i0 < e0; i0 += SMALL_THREADS * SMALL_R) {
-                double xv[SMALL_R], acc[SMALL_R];
-                int idx[SMALL_R];
-                bool xok = true;
-#pragma unroll
-                for (int r = 0; r < SMALL_R; ++r) {
-                    idx[r] = i0 + t + r * SMALL_THREADS;
-                    xv[r] = (idx[r] < e0) ? d.x[idx[r]] : 0.0;
-                    acc[r] = 0.0;
-                    xok = xok && x_fast_domain(xv[r]);
-                }
-                if (idx[0] < e0) {
-                    if (kfast && xok) {
-#pragma unroll 2
-                        for (int j = 0; j < n_kept; ++j) lorentz_step<SMALL_R, true>(kept[3 * j], kept[3 * j + 1], kept[3 * j + 2], xv, acc);
-                    } else {
-#pragma unroll 1
-                        for (int j = 0; j < n_kept; ++j) lorentz_step<SMALL_R, false>(kept[3 * j], kept[3 * j + 1], kept[3 * j + 2], xv, acc);
-                    }
-#pragma unroll
-                    for (int r = 0; r < SMALL_R; ++r)
-                        if (idx[r] < e0) {
-                            const double dd = __dsub_rn(acc[r], d.y[idx[r]]);  // :852
-                            resid[pos + idx[r] - s0] = __dmul_rn(dd, dd);
-                        }
-                }
-            }
+            int i0 = s0;
+            for (; e0 - i0 >= SMALL_THREADS * SMALL_R; i0 += SMALL_THREADS * SMALL_R)
+                small_mse_block<SMALL_R>(d.x, d.y, kept, n_kept, kfast, i0, e0, resid + pos - s0);
+            // the rest of the range with just enough points per thread (no thread evaluates padding)
+            const int rest = (e0 - i0 + SMALL_THREADS - 1) / SMALL_THREADS;
+            if (rest == 4) small_mse_block<4>(d.x, d.y, kept, n_kept, kfast, i0, e0, resid + pos - s0);
+            else if (rest == 3) small_mse_block<3>(d.x, d.y, kept, n_kept, kfast, i0, e0, resid + pos - s0);
+            else if (rest == 2) small_mse_block<2>(d.x, d.y, kept, n_kept, kfast, i0, e0, resid + pos - s0);
+            else if (rest == 1) small_mse_block<1>(d.x, d.y, kept, n_kept, kfast, i0, e0, resid + pos - s0);
             pos += e0 - s0;
         }
     }

@@ -120,6 +120,13 @@ class Deconvoluter:
         try:
             raise_for_status(st, _lib.last_error())
             sm, se, fi = self.smoothing_settings(), self.selection_settings(), self.fitting_settings()
+            if n == 1:  # the single-spectrum calls: no offset tables
+                params = np.empty((lib.mdb_batch_n_lorentzians(batch, 0), 3), dtype=np.float64)
+                peaks = np.empty((lib.mdb_batch_n_peaks(batch, 0), 3), dtype=np.int32)
+                mse1 = C.c_double()
+                raise_for_status(lib.mdb_batch_export(batch, None, None, None, C.byref(mse1), params.ctypes.data,
+                                                      peaks.ctypes.data), _lib.last_error())
+                return [Deconvolution(params, mse1.value, sm, se, fi, peaks)]
             # one bulk export for the whole batch; every Deconvolution holds views into the flat arrays
             tot_l, tot_p = C.c_size_t(), C.c_size_t()
             lib.mdb_batch_totals(batch, C.byref(tot_l), C.byref(tot_p))

@@ -956,11 +956,13 @@ def test_small_path_dense_peaks_short_inputs_and_errors():
             y = np.rint(rng.normal(0.0, 100.0, n)) if trial & 1 else rng.normal(0.0, 100.0, n)
             lo, hi = sorted(rng.uniform(0.5, 9.5, 2))
             sp = Spectrum(xs, y, (lo, hi))
-            for thr in (0.01, 5.0):
+            for thr, (iters, window) in ((0.01, (1, 3)), (5.0, (1, 3)), (0.01, (2, 9)), (0.01, (3, 41)), (0.5, (5, 2))):
+                if n < window // 2:
+                    continue  # the reference panics (moving_average.rs:62); covered by test_smoothing_short_inputs
                 dec = Deconvoluter()
-                dec.set_moving_average_smoother(1, 3)
+                dec.set_moving_average_smoother(iters, window)
                 dec.set_noise_score_selector(thr)
-                settings = O.Settings(smoothing_iterations=1, smoothing_window=3, threshold=thr)
+                settings = O.Settings(smoothing_iterations=iters, smoothing_window=window, threshold=thr)
                 r = O.deconvolute_spectrum(settings, xs, y, sp.signal_boundaries)
                 seen.add(r.status)
                 if r.status == O.OK:

@@ -59,10 +59,56 @@ for name, gpu, cpu, threads in rows:
     print(json.dumps({"bench": name, "gpu_ms_median": g_med * 1e3, "gpu_ms_min": g_min * 1e3, "oracle_ms_median": c_med * 1e3,
                       "oracle_threads": threads, "speedup_median": c_med / g_med}), flush=True)
 
-# where a single small spectrum spends its time on the device (CUDA events inside the library)
+# the same single-spectrum call without the Python wrappers on either side: the C ABI entry of the
+# library against the C entry of the oracle, buffers prepared once (what a Rust caller would see)
 import ctypes as C  # noqa: E402
 from metabodecon_rust_b200 import _lib  # noqa: E402
 lib = _lib.load()
+
+
+def raw_gpu(sp):
+    views = (_lib.SpectrumView * 1)()
+    views[0].chemical_shifts = sp.chemical_shifts.ctypes.data
+    views[0].intensities = sp.intensities.ctypes.data
+    views[0].len = sp.chemical_shifts.size
+    views[0].signal_boundaries[0], views[0].signal_boundaries[1] = sp.signal_boundaries
+    batch = C.c_void_p()
+
+    def call():
+        assert lib.mdb_deconvolute_spectra(dec._h, views, 1, _lib.MDB_MEM_HOST, C.byref(batch)) == 0
+        lib.mdb_batch_free(batch)
+    return call
+
+
+def raw_cpu(sp, parallel):
+    n = sp.intensities.size
+    cap = n // 2 + 1
+    st, _keep = O.Settings()._c()
+    lor = np.zeros((cap, 3))
+    sel = [np.zeros(cap, dtype=np.uintp) for _ in range(3)]
+    sm = np.empty(n)
+    res = O._Result()
+    x, y = np.ascontiguousarray(sp.chemical_shifts), np.ascontiguousarray(sp.intensities)
+    args = (C.byref(st), O._dp(x), O._dp(y), C.c_size_t(n), C.c_double(sp.signal_boundaries[0]),
+            C.c_double(sp.signal_boundaries[1]), C.c_int(parallel), O._dp(lor), O._sp(sel[0]), O._sp(sel[1]), O._sp(sel[2]),
+            O._dp(sm), C.byref(res))
+    fn = O.lib().orc_deconvolute_spectrum
+    keep = (st, _keep, lor, sel, sm, res, x, y)
+
+    def call():
+        fn(*args)
+        assert res.status == O.OK and keep
+    return call
+
+
+for name, sp, parallel in [("deconvolute_sim_spectrum [C ABI]", sim, False), ("parallel_deconvolute_sim_spectrum [C ABI]", sim, True),
+                           ("deconvolute_blood_spectrum [C ABI]", blood, False)]:
+    g_min, g_med = best_of(raw_gpu(sp), 50)
+    c_min, c_med = best_of(raw_cpu(sp, parallel), 5)
+    print(json.dumps({"bench": name, "gpu_ms_median": g_med * 1e3, "gpu_ms_min": g_min * 1e3, "oracle_ms_median": c_med * 1e3,
+                      "oracle_threads": cores if parallel else 1, "speedup_median": c_med / g_med}), flush=True)
+
+# where a single small spectrum spends its time on the device (CUDA events inside the library)
 lib.mdb_profile_enable(1)
 lib.mdb_profile_reset()
 for _ in range(20):
