@@ -107,7 +107,7 @@ __device__ __forceinline__ void sts_f64(uint32_t a, double v)
 // quotients are independent and interleave stage by stage (what lorentz_step does across points),
 // then join the running sum in index order -- the same operations per element as lorentz_step.
 template <int U>
-__device__ __forceinline__ void lorentz_multi(const double *p, const double x, double &acc)
+__device__ __forceinline__ void lorentz_multi_q(const double *p, const double x, double (&out)[U])
 {
     double a[U], den[U], r[U], e[U], q[U];
 #pragma unroll
@@ -134,6 +134,14 @@ __device__ __forceinline__ void lorentz_multi(const double *p, const double x, d
     for (int u = 0; u < U; ++u) e[u] = fma(-den[u], q[u], a[u]);
 #pragma unroll
     for (int u = 0; u < U; ++u) q[u] = fma(r[u], e[u], q[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) out[u] = q[u];
+}
+template <int U>
+__device__ __forceinline__ void lorentz_multi(const double *p, const double x, double &acc)
+{
+    double q[U];
+    lorentz_multi_q<U>(p, x, q);
 #pragma unroll
     for (int u = 0; u < U; ++u) acc = __dadd_rn(acc, q[u]);
 }
@@ -563,7 +571,17 @@ small_fused_kernel(const SpecDesc *__restrict__ sd, const SmallDesc *__restrict_
             double acc = 0.0;
             if (fast) {
                 int j = 0;
-                for (; j + 8 <= P; j += 8) lorentz_multi<8>(pin + 3 * j, x, acc);
+                if (P >= 8) {  // groups of 8: the ordered adds of one group run under the divisions of the next
+                    double qa[8], qb[8];
+                    lorentz_multi_q<8>(pin, x, qa);
+                    for (j = 8; j + 8 <= P; j += 8) {
+                        lorentz_multi_q<8>(pin + 3 * j, x, qb);
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) { acc = __dadd_rn(acc, qa[u]); qa[u] = qb[u]; }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) acc = __dadd_rn(acc, qa[u]);
+                }
                 if (j + 4 <= P) { lorentz_multi<4>(pin + 3 * j, x, acc); j += 4; }
                 if (j + 2 <= P) { lorentz_multi<2>(pin + 3 * j, x, acc); j += 2; }
                 if (j < P) lorentz_multi<1>(pin + 3 * j, x, acc);
