@@ -196,3 +196,46 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 text = open(os.path.join(base, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text and "mdb_oracle" not in text, f
+
+
+def test_deconvolution_json_and_messagepack_layouts(tmp_path):
+    """Serde-shaped output: camelCase JSON (serialized_deconvolution.rs:18-31) and
+    the compact MessagePack form of rmp_serde::to_vec (bindings/deconvolution.rs:97-117) -- structs as
+    arrays in field order, internally tagged enums with the tag first, Lorentzians as (sf, hw, maxp)."""
+    import json
+    import struct
+    from metabodecon_rust_b200 import Deconvolution
+    from metabodecon_rust_b200.exceptions import SerializationError
+
+    def f64(v):
+        return b"\xcb" + struct.pack(">d", v)
+
+    params = np.array([[12.5 * 0.25, 0.25 * 0.25, 5.0]])     # Lorentzian::new(sfhw, hw2, maxp) of (sf 12.5, hw 0.25, maxp 5)
+    dec = Deconvolution(params, 0.5, {"method": "MovingAverage", "iterations": 3, "windowSize": 3},
+                        {"method": "NoiseScoreFilter", "scoringMethod": {"method": "MinimumSum"}, "threshold": 5.0},
+                        {"method": "Analytical", "iterations": 10})
+    dec.write_bin(str(tmp_path / "d.bin"))
+    want = (b"\x95" + b"\x93\xadMovingAverage\x03\x03" + b"\x93\xb0NoiseScoreFilter\x91\xaaMinimumSum" + f64(5.0)
+            + b"\x92\xaaAnalytical\x0a" + f64(0.5) + b"\x91\x93" + f64(12.5) + f64(0.25) + f64(5.0))
+    assert (tmp_path / "d.bin").read_bytes() == want
+    back = Deconvolution.read_bin(str(tmp_path / "d.bin"))
+    assert back.mse == 0.5 and np.array_equal(back.parameters, params)
+    assert back.smoothing_settings == dec.smoothing_settings and back.selection_settings == dec.selection_settings
+    assert back.fitting_settings == dec.fitting_settings
+    # the named (map) form of rmp_serde::to_vec_named reads too
+    import msgpack
+    named = {"smoothingSettings": {"method": "Identity"}, "selectionSettings": {"method": "DetectorOnly"},
+             "fittingSettings": {"method": "Analytical", "iterations": 2}, "mse": 1.25,
+             "lorentzians": [{"sf": 2.0, "hw": 0.5, "maxp": -1.0}]}
+    (tmp_path / "n.bin").write_bytes(msgpack.packb(named))
+    got = Deconvolution.read_bin(str(tmp_path / "n.bin"))
+    assert got.smoothing_settings == {"method": "Identity"} and np.array_equal(got.parameters, [[1.0, 0.25, -1.0]])
+    # JSON: same content, camelCase keys, untransformed Lorentzians
+    dec.write_json(str(tmp_path / "d.json"))
+    js = json.loads((tmp_path / "d.json").read_text())
+    assert set(js) == {"smoothingSettings", "selectionSettings", "fittingSettings", "mse", "lorentzians"}
+    assert js["lorentzians"] == [{"sf": 12.5, "hw": 0.25, "maxp": 5.0}]
+    assert np.array_equal(Deconvolution.read_json(str(tmp_path / "d.json")).parameters, params)
+    (tmp_path / "bad.bin").write_bytes(b"\x93\x01\x02")
+    with pytest.raises(SerializationError):
+        Deconvolution.read_bin(str(tmp_path / "bad.bin"))
