@@ -9,6 +9,7 @@
 #include "kernels.cuh"
 #include "smooth_lanes.cuh"
 #include "small_fused.cuh"
+#include "smooth_stream.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -673,8 +674,19 @@ static mdb_status launch_smooth(cudaStream_t stream, const SpecDesc *d_desc, con
     int stride = 0, in_stages = 0;
     SmoothLanesFn fn = smooth_lanes_lookup(window, iters, S, sm_count(), &stride, &in_stages);
     const char *force = std::getenv("MDB_SMOOTH_GENERIC");
+    // A few long spectra: the latency form (smooth_stream.cuh), one CTA per spectrum.  From a couple
+    // of hundred spectra on the lane-packed kernel wins (it keeps 10 chains per warp going).
+    const char *stream_env = std::getenv("MDB_SMOOTH_STREAM");
+    bool streamable = iters >= 1 && iters <= STREAM_MAX_ITERS && window >= 1 && window <= 64 && S <= (size_t)2 * sm_count()
+                      && !(stream_env && stream_env[0] == '0') && !(force && force[0] == '1');
+    for (const SpecDesc &d : descs) streamable = streamable && d.n >= 4096;
     prof_begin(spans, MDB_KERNEL_SMOOTH, stream);
-    if (fn && aligned && !(force && force[0] == '1')) {
+    if (streamable) {
+        const size_t smem = smooth_stream_smem_bytes(iters);
+        CUDA_TRY(cudaFuncSetAttribute(smooth_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smooth_stream_kernel<<<(unsigned)S, STREAM_THREADS, smem, stream>>>(d_desc, iters, window);
+        LAUNCH_CHECK();
+    } else if (fn && aligned && !(force && force[0] == '1')) {
         const int groups = 32 / iters;  // spectra per warp: one lane per (spectrum, pass)
         const size_t smem = smooth_lanes_smem_bytes(stride, in_stages, groups);
         CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -248,6 +248,23 @@ def test_smoothing_tile_boundaries(n, iterations, window):
                      f"n={n} ({iterations},{window}) f64")
 
 
+@pytest.mark.parametrize("n", [4096, 4097, 6143, 8191, 8192, 8193, 10000, 2048 * 9 + 5, 50001])
+def test_smoothing_stream_kernel_ring_edges(n, monkeypatch):
+    """The latency form of K1 (smooth_stream.cuh: rings of 2 048 points in shared memory, taken by
+    calls of a few long spectra): lengths around multiples of the ring, every window parity, up to
+    12 passes; identical bits from the lane-packed kernel (MDB_SMOOTH_STREAM=0) and the oracle."""
+    rng = np.random.default_rng(n)
+    y = rng.normal(0, 1e4, n)
+    yi = np.rint(y)
+    for it, w in [(3, 3), (1, 2), (2, 2), (12, 3), (5, 8), (4, 9), (2, 33), (3, 64), (1, 7)]:
+        want = O.smooth_values(y, it, w)
+        assert_bit_equal(gpu_smooth(y, it, w), want, f"stream n={n} ({it},{w})")
+        assert_bit_equal(gpu_smooth(yi, it, w), O.smooth_values(yi, it, w), f"stream n={n} ({it},{w}) integer")
+        monkeypatch.setenv("MDB_SMOOTH_STREAM", "0")
+        assert_bit_equal(gpu_smooth(y, it, w), want, f"lanes n={n} ({it},{w})")
+        monkeypatch.delenv("MDB_SMOOTH_STREAM")
+
+
 @pytest.mark.parametrize("n", [5, 6, 7, 8, 17, 63, 64, 65])
 def test_smoothing_short_inputs(n):
     rng = np.random.default_rng(n)
