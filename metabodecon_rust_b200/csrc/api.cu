@@ -10,6 +10,7 @@
 #include "smooth_lanes.cuh"
 #include "small_fused.cuh"
 #include "smooth_stream.cuh"
+#include "fit_wide.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -957,7 +958,7 @@ static mdb_status stage_b(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
     CUDA_TRY(ws.h_fdesc.ensure(S * sizeof(FitDesc)));
     CUDA_TRY(ws.segs.ensure(std::max<size_t>(n_seg, 1) * sizeof(Segment)));
     CUDA_TRY(ws.h_segs.ensure(std::max<size_t>(n_seg, 1) * sizeof(Segment)));
-    CUDA_TRY(ws.fit_state.ensure(11 * align_up(P, 16) * 8));
+    CUDA_TRY(ws.fit_state.ensure(14 * align_up(P, 16) * 8));  // 11 stencil rows + 3 rows of rescaled y (fit_wide.cuh)
     CUDA_TRY(ws.par_a.ensure(P * 24));
     CUDA_TRY(ws.par_b.ensure(P * 24));
     CUDA_TRY(ws.lor.ensure(P * 24));
@@ -997,7 +998,31 @@ static mdb_status stage_b(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
         // to end (it holds every SM slot for the whole fit, which starves the other chunk streams),
         // so it stays an experiment.
         const char *persistent = std::getenv("MDB_FIT_PERSISTENT");
-        if (trace || !(persistent && persistent[0] == '1')) {
+        // A few spectra: one pass = superposition per (stencil point, peak) + solve per peak
+        // (fit_wide.cuh); three times the CTAs and 8 Lorentzians in flight per thread.
+        long long fit_blocks = 0;
+        for (size_t s = 0; s < S; ++s) fit_blocks += (ck.fdesc[s].n_peaks + FIT_THREADS - 1) / FIT_THREADS;
+        const char *wide_env = std::getenv("MDB_FIT_WIDE");
+        const bool wide = fit_blocks * 3 <= sm_count() && !(wide_env && wide_env[0] == '0') && !(persistent && persistent[0] == '1');
+        if (wide) {
+            const long long yn_stride = (long long)align_up(P, 16);
+            double *yn = ws.fit_state.as<double>() + 11 * yn_stride;
+            dim3 grid3(grid.x, grid.y, 3);
+            for (int it = 0; it < iters; ++it) {
+                double evals = 0.0;
+                for (size_t s = 0; s < S; ++s)
+                    if (it < ck.fdesc[s].n_iters) evals += 3.0 * (double)ck.fdesc[s].n_peaks * (double)ck.fdesc[s].n_peaks;
+                prof_begin(&ck.spans, MDB_KERNEL_FIT_ITER, ws.stream);
+                fit_wide_superpose_kernel<<<grid3, FIT_THREADS, LOR_SMEM_BYTES, ws.stream>>>(d_fd, st, yn, yn_stride, it);
+                LAUNCH_CHECK();
+                fit_wide_solve_kernel<<<grid, FIT_THREADS, 0, ws.stream>>>(d_fd, st, yn, yn_stride, it);
+                LAUNCH_CHECK();
+                prof_end(&ck.spans, ws.stream, evals);
+                if (trace)
+                    CUDA_TRY(counted_memcpy_async(trace + (size_t)(it + 1) * n_trace, (it & 1) ? st.pa : st.pb, n_trace * 24,
+                                             cudaMemcpyDeviceToHost, ws.stream));
+            }
+        } else if (trace || !(persistent && persistent[0] == '1')) {
             // one launch per refinement pass (needed for the per-pass trace of mdb_stage_fit)
             for (int it = 0; it < iters; ++it) {
                 double evals = 0.0;  // E_fit of this pass = sum of 3 * P_s^2 over the spectra still iterating

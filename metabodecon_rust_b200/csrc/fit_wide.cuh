@@ -1,0 +1,130 @@
+// fit_wide.cuh -- K6 for a FEW spectra: one refinement pass as two launches.
+//
+// fit_iter_kernel gives every peak one thread that walks all P Lorentzians at its three stencil
+// points; a single spectrum of ~1 000 peaks is then 8 CTAs, each thread a chain of 1 000 ordered
+// evaluations, and a pass takes 82 us however idle the other 140 SMs are.  Here a pass is split:
+//   fit_wide_superpose_kernel  one thread per (stencil point, peak): three times the CTAs, and each
+//                              thread interleaves 8 consecutive Lorentzians at its ONE point
+//                              (lorentz_multi_q) instead of 3 points at one Lorentzian; it ends with
+//                              the ratio and the rescaled stencil value (fitter_analytical.rs:42-54);
+//   fit_wide_solve_kernel      one thread per peak: mirror and re-solve (:55-64).
+// The sum over j stays one ordered chain per (point, peak); results are bit-identical to
+// fit_iter_kernel (tests: the per-pass traces of mdb_stage_fit run through this form, batches
+// through the other, both against the oracle).
+#pragma once
+#include "kernels.cuh"
+#include "small_fused.cuh"
+
+namespace mdb {
+
+// Ordered superposition of Lorentzians [0, p) at ONE point per thread; tiles, barriers and the
+// fast-domain test as in superpose_tiles.  All threads of the CTA must call.
+template <int T>
+__device__ __forceinline__ void superpose_tiles_point(unsigned char *smem, const double *__restrict__ src, int p,
+                                                      const double x, double &acc, uint32_t &tc)
+{
+    double(*tile)[3 * LOR_TILE] = reinterpret_cast<double(*)[3 * LOR_TILE]>(smem);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + 2 * 3 * LOR_TILE * sizeof(double));
+    const int tid = threadIdx.x;
+    if (tc == 0) {
+        if (tid == 0) {
+            mbarrier_init(&bar[0], 1);
+            mbarrier_init(&bar[1], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+    }
+    const bool x_ok = x_fast_domain(x);
+    const int ntiles = (p + LOR_TILE - 1) / LOR_TILE;
+    auto issue = [&](int t) {
+        const int cnt = min(LOR_TILE, p - t * LOR_TILE);
+        const double *g = src + 3ll * t * LOR_TILE;
+        const uint32_t slot = (tc + (uint32_t)t) & 1u;
+        double *buf = tile[slot];
+        const uint32_t bytes = (uint32_t)cnt * 24u, bulk = bytes & ~15u;
+        if (bytes & 8u) buf[3 * cnt - 1] = __ldcg(g + 3 * cnt - 1);
+        mbarrier_expect_tx(&bar[slot], bulk);
+        if (bulk) tma_bulk_g2s(buf, g, bulk, &bar[slot]);
+    };
+    if (tid == 0 && ntiles > 0) issue(0);
+    for (int t = 0; t < ntiles; ++t) {
+        const int cnt = min(LOR_TILE, p - t * LOR_TILE);
+        const uint32_t seq = tc + (uint32_t)t, slot = seq & 1u;
+        if (tid == 0 && t + 1 < ntiles) issue(t + 1);
+        mbarrier_wait(&bar[slot], (seq >> 1) & 1u);
+        const double *s = tile[slot];
+        bool ok = x_ok;
+        for (int j = tid; j < cnt; j += T) ok = ok && params_fast_domain(s[3 * j], s[3 * j + 1], s[3 * j + 2]);
+        if (__syncthreads_and(ok)) {
+            int j = 0;
+            if (cnt >= 8) {  // groups of 8: the ordered adds of one group run under the divisions of the next
+                double qa[8], qb[8];
+                lorentz_multi_q<8>(s, x, qa);
+                for (j = 8; j + 8 <= cnt; j += 8) {
+                    lorentz_multi_q<8>(s + 3 * j, x, qb);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) { acc = __dadd_rn(acc, qa[u]); qa[u] = qb[u]; }
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) acc = __dadd_rn(acc, qa[u]);
+            }
+            if (j + 4 <= cnt) { lorentz_multi<4>(s + 3 * j, x, acc); j += 4; }
+            if (j + 2 <= cnt) { lorentz_multi<2>(s + 3 * j, x, acc); j += 2; }
+            if (j < cnt) lorentz_multi<1>(s + 3 * j, x, acc);
+        } else {
+            const double xs[1] = {x};
+            double as[1] = {acc};
+#pragma unroll 1
+            for (int j = 0; j < cnt; ++j) lorentz_step<1, false>(s[3 * j], s[3 * j + 1], s[3 * j + 2], xs, as);
+            acc = as[0];
+        }
+        __syncthreads();
+    }
+    tc += (uint32_t)ntiles;
+}
+
+// grid (ceil(max_peaks / FIT_THREADS), spectra, 3): blockIdx.z is the stencil point
+__global__ void __launch_bounds__(FIT_THREADS)
+fit_wide_superpose_kernel(const FitDesc *__restrict__ fd, FitState st, double *__restrict__ yn, long long yn_stride, int it)
+{
+    extern __shared__ __align__(128) unsigned char lor_smem[];
+    const FitDesc f = fd[blockIdx.y];
+    if (blockIdx.x * FIT_THREADS >= f.n_peaks || it >= f.n_iters) return;
+    const double *__restrict__ pin = (it & 1) ? st.pb : st.pa;
+    const int q = blockIdx.z;
+    const double *__restrict__ ox = q == 0 ? st.ox1 : (q == 1 ? st.ox2 : st.ox3);
+    const double *__restrict__ oy = q == 0 ? st.oy1 : (q == 1 ? st.oy2 : st.oy3);
+    const double *__restrict__ sy = q == 0 ? st.sy1 : (q == 1 ? st.sy2 : st.sy3);
+    const int k = blockIdx.x * FIT_THREADS + threadIdx.x;
+    const bool active = k < f.n_peaks;
+    const long long g = f.off + (active ? k : 0);
+    const double x = ox[g];
+    double acc = 0.0;
+    uint32_t tc = 0;
+    superpose_tiles_point<FIT_THREADS>(lor_smem, pin + 3 * f.off, f.n_peaks, x, acc, tc);
+    if (!active) return;
+    // ratio = y_orig / superposition (:42-47); y_k = y_k * ratio_k (:52-54)
+    yn[(long long)q * yn_stride + g] = __dmul_rn(sy[g], __ddiv_rn(oy[g], acc));
+}
+
+// grid (ceil(max_peaks / FIT_THREADS), spectra)
+__global__ void __launch_bounds__(FIT_THREADS)
+fit_wide_solve_kernel(const FitDesc *__restrict__ fd, FitState st, const double *__restrict__ yn, long long yn_stride, int it)
+{
+    const FitDesc f = fd[blockIdx.y];
+    const int k = blockIdx.x * FIT_THREADS + threadIdx.x;
+    if (k >= f.n_peaks || it >= f.n_iters) return;
+    double *__restrict__ pout = (it & 1) ? st.pa : st.pb;
+    const long long g = f.off + k;
+    Stencil p;
+    p.x1 = st.sx1[g]; p.x2 = st.ox2[g]; p.x3 = st.sx3[g];
+    p.y1 = yn[g]; p.y2 = yn[yn_stride + g]; p.y3 = yn[2 * yn_stride + g];
+    mirror_shoulder(p);
+    st.sx1[g] = p.x1; st.sx3[g] = p.x3;
+    st.sy1[g] = p.y1; st.sy2[g] = p.y2; st.sy3[g] = p.y3;
+    double sfhw, hw2, maxp;
+    solve_stencil(p, sfhw, hw2, maxp);  // :61-64
+    pout[3 * g] = sfhw; pout[3 * g + 1] = hw2; pout[3 * g + 2] = maxp;
+}
+
+}  // namespace mdb

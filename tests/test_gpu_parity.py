@@ -473,6 +473,33 @@ def test_fit_bit_exact_synthetic(iterations):
     assert_bit_equal(got, want, "synthetic retained")
 
 
+def test_fit_wide_and_per_peak_forms_agree(blood_arrays, monkeypatch):
+    """A call of a few spectra runs a refinement pass as superposition per (stencil point, peak) +
+    solve per peak (fit_wide.cuh); MDB_FIT_WIDE=0 keeps fit_iter_kernel (one thread per peak).  Same
+    traces, pass by pass, and both equal to the oracle's -- also with values outside div_fast's domain."""
+    x, y = blood_arrays
+    r = O.deconvolute_spectrum(O.Settings(ignore_regions=[(4.7, 4.9)]), x, y, (11.8, -2.2))
+    want, wtr = O.fit_lorentzian(x, y, r.peaks, 4, trace=True)
+    wide, tr_wide = gpu_fit(x, y, r.peaks, 4)
+    monkeypatch.setenv("MDB_FIT_WIDE", "0")
+    narrow, tr_narrow = gpu_fit(x, y, r.peaks, 4)
+    monkeypatch.delenv("MDB_FIT_WIDE")
+    assert_bit_equal(tr_wide, wtr, "wide form, trace")
+    assert_bit_equal(tr_narrow, wtr, "per-peak form, trace")
+    assert_bit_equal(wide, want, "wide form, retained")
+    assert_bit_equal(narrow, want, "per-peak form, retained")
+    # a few peaks, one of them on a huge intensity (quotients beyond 2^300: the IEEE division loop)
+    n = 4096
+    xs = synth.axis(n)
+    ys = synth.spectrum(77, n=n, k=30, hw_range=(8e-3, 5e-2), x=xs)
+    ys[2000:2003] = [1e200, 3e200, 2e200]
+    peaks = np.array([[1999, 2001, 2003], [999, 1001, 1003], [3000, 3002, 3004]], dtype=np.int64)
+    want, wtr = O.fit_lorentzian(xs, ys, peaks, 3, trace=True)
+    got, tr = gpu_fit(xs, ys, peaks, 3)
+    nan = np.isnan(wtr)
+    assert_bit_equal(np.where(nan, 0.0, tr), np.where(nan, 0.0, wtr), "wide form, out-of-domain values")
+
+
 def test_fit_many_peaks_tiles():
     # more peaks than one shared-memory tile (LOR_TILE = 512) and a ragged last block
     n = 131072
