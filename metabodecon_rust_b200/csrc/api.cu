@@ -675,10 +675,12 @@ static mdb_status launch_smooth(cudaStream_t stream, const SpecDesc *d_desc, con
     int stride = 0, in_stages = 0;
     SmoothLanesFn fn = smooth_lanes_lookup(window, iters, S, sm_count(), &stride, &in_stages);
     const char *force = std::getenv("MDB_SMOOTH_GENERIC");
-    // A few long spectra: the latency form (smooth_stream.cuh), one CTA per spectrum.  From a couple
-    // of hundred spectra on the lane-packed kernel wins (it keeps 10 chains per warp going).
+    // A few long spectra: the latency form (smooth_stream.cuh), one CTA per spectrum.  Only for launches
+    // of up to 32 spectra: its CTAs hold 66 KB of shared memory each for the whole smoothing, which in
+    // the chunk pipeline (40+ spectra per chunk, eight chunks in flight) would crowd the FP64 kernels
+    // of the other chunks off the SMs; there the lane-packed kernel (10 chains per warp) stays.
     const char *stream_env = std::getenv("MDB_SMOOTH_STREAM");
-    bool streamable = iters >= 1 && iters <= STREAM_MAX_ITERS && window >= 1 && window <= 64 && S <= (size_t)2 * sm_count()
+    bool streamable = iters >= 1 && iters <= STREAM_MAX_ITERS && window >= 1 && window <= 64 && S <= 32
                       && !(stream_env && stream_env[0] == '0') && !(force && force[0] == '1');
     for (const SpecDesc &d : descs) streamable = streamable && d.n >= 4096;
     prof_begin(spans, MDB_KERNEL_SMOOTH, stream);
