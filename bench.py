@@ -171,6 +171,7 @@ def main():
     ap.add_argument("--sup-points", type=int, default=1 << 24, help="config 4: grid points (whole job, sharded over the GPUs)")
     ap.add_argument("--sup-lorentzians", type=int, default=20000, help="config 4: Lorentzians")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-small-spectra", action="store_true", help="skip the 2 048-point small-spectrum measurements")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--host-memory", default="pinned", choices=["pinned", "pageable"],
                     help="host buffers of the e2e measurement (pageable = what NumPy callers hand over)")
@@ -368,6 +369,52 @@ def main():
             del src, dst
         torch.cuda.empty_cache()
 
+    # ---- the small-spectrum path (one fused launch per call, csrc/small_fused.cuh): 2 048-point spectra,
+    # the size of the reference's `sim` benchmark set (benches/deconvoluter.rs:8-52).  Latency of one
+    # call from host memory through the C ABI, and spectra/s for 2 000 of them in one call, each beside
+    # the oracle port on the host cores.  Rank 0 at N = 1 only; not the headline metric.
+    small = None
+    if not args.no_small_spectra and world == 1:
+        import oracle as O   # the checker beside the product, as in the cpu_baseline leg
+        import synth
+        n_s, count_s = 2048, 2000
+        xs = synth.axis(n_s)
+        ys_small = np.stack([synth.spectrum(7000 + s, n=n_s, k=30, hw_range=(8e-3, 5e-2), x=xs) for s in range(16)])
+        ys_all = np.ascontiguousarray(np.tile(ys_small, (count_s // 16, 1)))
+        views_s = (_lib.SpectrumView * count_s)()
+        for i in range(count_s):
+            views_s[i].chemical_shifts = xs.ctypes.data
+            views_s[i].intensities = ys_all[i].ctypes.data
+            views_s[i].len = n_s
+            views_s[i].signal_boundaries[0], views_s[i].signal_boundaries[1] = SB
+
+        def small_call(k):
+            b = C.c_void_p()
+            assert lib.mdb_deconvolute_spectra(dec, views_s, k, _lib.MDB_MEM_HOST, C.byref(b)) == 0, _lib.last_error()
+            lib.mdb_batch_free(b)
+
+        def median_ms(fn, reps):
+            fn()
+            ts = []
+            for _ in range(reps):
+                t0 = time.perf_counter()
+                fn()
+                ts.append(time.perf_counter() - t0)
+            return 1e3 * float(np.median(ts))
+
+        lat_ms = median_ms(lambda: small_call(1), 200)
+        batch_ms = median_ms(lambda: small_call(count_s), 10)
+        O.use_all_cores()
+        cpu1_ms = median_ms(lambda: O.deconvolute_spectrum(O.Settings(), xs, ys_all[0], SB), 20)
+        t0 = time.perf_counter()
+        st_s, *_ = O.par_deconvolute_spectra(O.Settings(), xs, ys_all, SB)
+        cpu_batch_ms = 1e3 * (time.perf_counter() - t0)
+        assert st_s == O.OK
+        small = {"workload": f"{n_s}-point spectra, default settings, host memory through the C ABI",
+                 "single_call_ms": lat_ms, "single_call_oracle_ms": cpu1_ms,
+                 "spectra_per_s": count_s / (batch_ms / 1e3), "spectra_per_call": count_s,
+                 "oracle_spectra_per_s": count_s / (cpu_batch_ms / 1e3)}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -473,6 +520,7 @@ def main():
         "kernel_ms_serial_step": {k: v["ms"] for k, v in prof.items() if v["launches"]},
         "serial_step_ms": ms_serial, "roofline_pass": f"one extra step, chunks of {ROOFLINE_CHUNK} spectra, one chunk at a time",
         "superposition_vec": sup,
+        "small_spectra": small,
         "smooth_launch_size_sweep": None if smooth_sat is None else
         [dict(e, frac_of_hbm_peak=e["gb_per_s"] / hbm_peak) for e in smooth_sat],
         "cpu_baseline": cpu, "parity_sample": parity,
