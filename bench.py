@@ -153,10 +153,26 @@ def run_reference(args, rank, world):
         "gpu_launches": 0, "clocks": None,
         "note": "oracle/ C port of the reference path (the Rust reference cannot be built here: no cargo/rustc)",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_JSON_OUT = None
+
+
+def emit(line: dict) -> None:
+    """The one JSON line, on the process's original stdout."""
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    # stdout carries the one JSON line and nothing else: libraries that print there (NCCL's version
+    # banner does) are sent to stderr by swapping file descriptor 1 before anything is loaded
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -525,7 +541,7 @@ def main():
         [dict(e, frac_of_hbm_peak=e["gb_per_s"] / hbm_peak) for e in smooth_sat],
         "cpu_baseline": cpu, "parity_sample": parity,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
