@@ -20,7 +20,7 @@ namespace mdb {
 // Ordered superposition of Lorentzians [0, p) at ONE point per thread; tiles, barriers and the
 // fast-domain test as in superpose_tiles.  All threads of the CTA must call.
 template <int T>
-__device__ __forceinline__ void superpose_tiles_point(unsigned char *smem, const double *__restrict__ src, int p,
+__device__ __forceinline__ void superpose_tiles_point(unsigned char *smem, double *qs, const double *__restrict__ src, int p,
                                                       const double x, double &acc, uint32_t &tc)
 {
     double(*tile)[3 * LOR_TILE] = reinterpret_cast<double(*)[3 * LOR_TILE]>(smem);
@@ -57,16 +57,32 @@ __device__ __forceinline__ void superpose_tiles_point(unsigned char *smem, const
         for (int j = tid; j < cnt; j += T) ok = ok && params_fast_domain(s[3 * j], s[3 * j + 1], s[3 * j + 2]);
         if (__syncthreads_and(ok)) {
             int j = 0;
-            if (cnt >= 8) {  // groups of 8: the ordered adds of one group run under the divisions of the next
-                double qa[8], qb[8];
-                lorentz_multi_q<8>(s, x, qa);
-                for (j = 8; j + 8 <= cnt; j += 8) {
-                    lorentz_multi_q<8>(s + 3 * j, x, qb);
+            if (cnt >= 8) {
+                // Groups of 8 Lorentzians.  The quotients of a group go through the thread's own column
+                // of shared memory and join the ordered sum one group later: with the eight division
+                // chains all ending in a store, ptxas gives them equal priority and interleaves them
+                // (ending in the ordered adds they get descending priority and are emitted one after
+                // the other -- measured: 8 MUFU.RCP64H spread over 340 instructions, 20 % issue rate),
+                // and the adds of the previous group fill their stalls.
+                double q[8];
+                int b = 0;
+                lorentz_multi_q<8>(s, x, q);
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) { acc = __dadd_rn(acc, qa[u]); qa[u] = qb[u]; }
+                for (int u = 0; u < 8; ++u) qs[(0 * 8 + u) * T + tid] = q[u];
+#pragma unroll 1
+                for (j = 8; j + 8 <= cnt; j += 8) {
+                    double pq[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) pq[u] = qs[(b * 8 + u) * T + tid];
+                    lorentz_multi_q<8>(s + 3 * j, x, q);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) qs[((b ^ 1) * 8 + u) * T + tid] = q[u];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) acc = __dadd_rn(acc, pq[u]);
+                    b ^= 1;
                 }
 #pragma unroll
-                for (int u = 0; u < 8; ++u) acc = __dadd_rn(acc, qa[u]);
+                for (int u = 0; u < 8; ++u) acc = __dadd_rn(acc, qs[(b * 8 + u) * T + tid]);
             }
             if (j + 4 <= cnt) { lorentz_multi<4>(s + 3 * j, x, acc); j += 4; }
             if (j + 2 <= cnt) { lorentz_multi<2>(s + 3 * j, x, acc); j += 2; }
@@ -88,6 +104,7 @@ __global__ void __launch_bounds__(FIT_THREADS)
 fit_wide_superpose_kernel(const FitDesc *__restrict__ fd, FitState st, double *__restrict__ yn, long long yn_stride, int it)
 {
     extern __shared__ __align__(128) unsigned char lor_smem[];
+    __shared__ double quot_smem[2 * 8 * FIT_THREADS];  // [buffer][slot][thread]: a column per thread, conflict-free
     const FitDesc f = fd[blockIdx.y];
     if (blockIdx.x * FIT_THREADS >= f.n_peaks || it >= f.n_iters) return;
     const double *__restrict__ pin = (it & 1) ? st.pb : st.pa;
@@ -101,7 +118,7 @@ fit_wide_superpose_kernel(const FitDesc *__restrict__ fd, FitState st, double *_
     const double x = ox[g];
     double acc = 0.0;
     uint32_t tc = 0;
-    superpose_tiles_point<FIT_THREADS>(lor_smem, pin + 3 * f.off, f.n_peaks, x, acc, tc);
+    superpose_tiles_point<FIT_THREADS>(lor_smem, quot_smem, pin + 3 * f.off, f.n_peaks, x, acc, tc);
     if (!active) return;
     // ratio = y_orig / superposition (:42-47); y_k = y_k * ratio_k (:52-54)
     yn[(long long)q * yn_stride + g] = __dmul_rn(sy[g], __ddiv_rn(oy[g], acc));
