@@ -884,11 +884,12 @@ static mdb_status stage_a(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
         const size_t smem = (size_t)4 * ck.max_tiles * sizeof(int);
         if ((int)smem + 1024 > smem_optin_limit())
             return fail(MDB_ERR_UNSUPPORTED, "spectrum too long for the selection kernel's shared-memory masks");
+        const bool few = S <= 8;  // few spectra: 32 warps per spectrum instead of 8
+        auto kern = few ? select_kernel<1024> : select_kernel<SELECT_THREADS>;
         if (smem > 40 * 1024)
-            CUDA_TRY(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         prof_begin(&ck.spans, MDB_KERNEL_SELECT, ws.stream);
-        select_kernel<<<(unsigned)S, SELECT_THREADS, smem, ws.stream>>>(d_desc, ws.sel_out.as<SelectOut>(),
-                                                                       dc.selection.kind);
+        kern<<<(unsigned)S, few ? 1024 : SELECT_THREADS, smem, ws.stream>>>(d_desc, ws.sel_out.as<SelectOut>(), dc.selection.kind);
         LAUNCH_CHECK();
         prof_end(&ck.spans, ws.stream, (double)S);
     }
