@@ -239,3 +239,28 @@ def test_deconvolution_json_and_messagepack_layouts(tmp_path):
     (tmp_path / "bad.bin").write_bytes(b"\x93\x01\x02")
     with pytest.raises(SerializationError):
         Deconvolution.read_bin(str(tmp_path / "bad.bin"))
+
+
+def test_spectrum_json_and_messagepack_round_trip(tmp_path):
+    """Spectrum storage in the reference's serde shape (spectrum/serialized_spectrum.rs:17-62): the axis
+    travels as (first, last, size) and is rebuilt as first + i * step."""
+    import json
+    n = 64
+    x = 10.0 - np.arange(n) * (10.0 / (n - 1))
+    y = np.sin(np.arange(n) * 0.3) * 100.0
+    sp = Spectrum(x, y, (1.0, 9.0))
+    sp.nucleus, sp.frequency = "13C", 150.9
+    sp.reference_compound = {"chemical_shift": 10.0, "index": 0, "name": "TMS"}
+    sp.write_json(str(tmp_path / "s.json"))
+    js = json.loads((tmp_path / "s.json").read_text())
+    assert set(js) == {"spectrumBoundaries", "signalBoundaries", "size", "nucleus", "frequency", "referenceCompound", "intensities"}
+    assert js["size"] == n and js["nucleus"] == "13C" and js["referenceCompound"] == {"chemicalShift": 10.0, "index": 0, "name": "TMS"}
+    sp.write_bin(str(tmp_path / "s.bin"))
+    for back in (Spectrum.read_json(str(tmp_path / "s.json")), Spectrum.read_bin(str(tmp_path / "s.bin"))):
+        assert np.array_equal(back.intensities, y) and back.signal_boundaries == sp.signal_boundaries
+        want_x = x[0] + np.arange(n) * ((x[-1] - x[0]) / (n - 1.0))       # serialized_spectrum.rs:54-57
+        assert np.array_equal(back.chemical_shifts, want_x)
+        assert back.nucleus == "13C" and back.frequency == 150.9 and back.reference_compound["name"] == "TMS"
+    (tmp_path / "bad.json").write_text('{"size": 3}')
+    with pytest.raises(exceptions.SerializationError):
+        Spectrum.read_json(str(tmp_path / "bad.json"))
