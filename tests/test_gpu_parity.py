@@ -1089,3 +1089,28 @@ def test_concurrent_callers_share_one_deconvoluter():
             assert np.array_equal(a.peaks, b.peaks)
             assert_bit_equal(b.parameters, a.parameters, f"thread {t}")
             assert a.mse == b.mse
+    # the same through the small-spectrum path (one fused launch per call, result slots in pinned memory)
+    xs = synth.axis(2048)
+    small = [[Spectrum(xs, synth.spectrum(1200 + 10 * t + s, n=2048, k=30, hw_range=(8e-3, 5e-2), x=xs), (-2.2, 11.8))
+              for s in range(1 + t)] for t in range(4)]
+    want = [dec.deconvolute_spectra(b) for b in small]
+    got, errors = [None] * 4, []
+
+    def work_small(t):
+        try:
+            for _ in range(25):
+                got[t] = dec.deconvolute_spectra(small[t])
+        except Exception as err:  # noqa: BLE001
+            errors.append(err)
+
+    threads = [threading.Thread(target=work_small, args=(t,)) for t in range(4)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
+    for t in range(4):
+        for a, b in zip(want[t], got[t]):
+            assert np.array_equal(a.peaks, b.peaks)
+            assert_bit_equal(b.parameters, a.parameters, f"small path, thread {t}")
+            assert a.mse == b.mse
