@@ -1006,7 +1006,7 @@ static mdb_status stage_b(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
         long long fit_blocks = 0;
         for (size_t s = 0; s < S; ++s) fit_blocks += (ck.fdesc[s].n_peaks + FIT_THREADS - 1) / FIT_THREADS;
         const char *wide_env = std::getenv("MDB_FIT_WIDE");
-        const bool wide = fit_blocks * 3 <= sm_count() && !(wide_env && wide_env[0] == '0') && !(persistent && persistent[0] == '1');
+        const bool wide = fit_blocks <= sm_count() && !(wide_env && wide_env[0] == '0') && !(persistent && persistent[0] == '1');
         if (wide) {
             const long long yn_stride = (long long)align_up(P, 16);
             double *yn = ws.fit_state.as<double>() + 11 * yn_stride;
