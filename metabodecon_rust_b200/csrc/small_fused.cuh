@@ -1,10 +1,11 @@
 // small_fused.cuh -- the whole deconvolution of a SMALL spectrum in ONE launch.
 //
-// The chunked pipeline of api.cu (detect -> select -> host round trip -> fit_init -> fit_iter x I_f
-// -> retain -> superposition -> mse_reduce) is built for batches of 2^17-point spectra: ~20 launches
+// The chunked pipeline of api.cu (smooth -> detect -> select -> host round trip -> fit_init ->
+// fit_iter x I_f -> retain -> superposition -> mse_reduce) is built for batches of 2^17-point spectra: ~20 launches
 // and two host synchronisations per chunk, which is all a 2 048-point spectrum (the reference's
 // `sim` bench set, benches/deconvoluter.rs:8-52) ever pays for.  Here one CTA owns one spectrum and
-// walks the same stages back to back with the whole second difference resident in shared memory:
+// walks the same stages back to back -- the moving average included, one warp with a lane per pass --
+// with the whole smoothed row and second difference resident in shared memory:
 // no tiles, no halos, no cold fallbacks, no counts travelling to the host between stages; results
 // go straight into a page-locked host slot (zero-copy stores), so the call is one H2D copy, this
 // launch and one stream synchronisation.
