@@ -1011,12 +1011,22 @@ static mdb_status stage_b(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
             const long long yn_stride = (long long)align_up(P, 16);
             double *yn = ws.fit_state.as<double>() + 11 * yn_stride;
             dim3 grid3(grid.x, grid.y, 3);
+            // MDB_FIT_WIDE=1 selects the instruction-parallel form (8 Lorentzians per thread), anything else
+            // the thread-parallel one (producers / accumulators)
+            const bool wide2 = !(wide_env && wide_env[0] == '1');
+            if (wide2)
+                CUDA_TRY(cudaFuncSetAttribute(fit_wide2_superpose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WIDE2_SMEM));
             for (int it = 0; it < iters; ++it) {
                 double evals = 0.0;
                 for (size_t s = 0; s < S; ++s)
                     if (it < ck.fdesc[s].n_iters) evals += 3.0 * (double)ck.fdesc[s].n_peaks * (double)ck.fdesc[s].n_peaks;
                 prof_begin(&ck.spans, MDB_KERNEL_FIT_ITER, ws.stream);
-                fit_wide_superpose_kernel<<<grid3, FIT_THREADS, LOR_SMEM_BYTES, ws.stream>>>(d_fd, st, yn, yn_stride, it);
+                if (wide2) {
+                    dim3 g2((unsigned)((ck.max_peaks + WIDE2_CHAINS - 1) / WIDE2_CHAINS), (unsigned)S, 3);
+                    fit_wide2_superpose_kernel<<<g2, WIDE2_THREADS, WIDE2_SMEM, ws.stream>>>(d_fd, st, yn, yn_stride, it);
+                } else {
+                    fit_wide_superpose_kernel<<<grid3, FIT_THREADS, LOR_SMEM_BYTES, ws.stream>>>(d_fd, st, yn, yn_stride, it);
+                }
                 LAUNCH_CHECK();
                 fit_wide_solve_kernel<<<grid, FIT_THREADS, 0, ws.stream>>>(d_fd, st, yn, yn_stride, it);
                 LAUNCH_CHECK();

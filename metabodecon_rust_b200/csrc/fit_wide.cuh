@@ -124,6 +124,106 @@ fit_wide_superpose_kernel(const FitDesc *__restrict__ fd, FitState st, double *_
     yn[(long long)q * yn_stride + g] = __dmul_rn(sy[g], __ddiv_rn(oy[g], acc));
 }
 
+// ---------------------------------------------------------------------------------------------
+// The superposition step once more, with thread-level instead of instruction-level parallelism.
+// A chain (stencil point, peak) is an ordered sum over all P Lorentzians, but only the SUM is
+// ordered: the quotients are independent.  A CTA owns WIDE2_CHAINS chains; seven producer threads
+// per chain evaluate 8 quotients each of a 56-Lorentzian tile into shared memory, and one
+// accumulator thread per chain adds the finished tile in index order while the producers are
+// already on the next one (two tile buffers, named barriers full[b] / empty[b]).  3 P chains x P
+// quotients then keep ~50 SMs x 14 producer warps busy instead of 24 SMs x 4 warps of 8-deep ILP.
+// Every quotient and every addition is the same operation as in fit_iter_kernel.
+// ---------------------------------------------------------------------------------------------
+constexpr int WIDE2_CHAINS = 64;
+constexpr int WIDE2_PHASES = 7;
+constexpr int WIDE2_TILE = 8 * WIDE2_PHASES;                          // Lorentzians per tile
+constexpr int WIDE2_THREADS = WIDE2_CHAINS * (1 + WIDE2_PHASES);      // 64 accumulators + 448 producers
+constexpr size_t WIDE2_SMEM = (size_t)2 * WIDE2_TILE * WIDE2_CHAINS * sizeof(double);
+
+// grid (ceil(max_peaks / WIDE2_CHAINS), spectra, 3): blockIdx.z is the stencil point
+__global__ void __launch_bounds__(WIDE2_THREADS)
+fit_wide2_superpose_kernel(const FitDesc *__restrict__ fd, FitState st, double *__restrict__ yn, long long yn_stride, int it)
+{
+    extern __shared__ __align__(16) unsigned char wide2_smem[];
+    double *quot = reinterpret_cast<double *>(wide2_smem);            // [buffer][slot in tile][chain]
+    const FitDesc f = fd[blockIdx.y];
+    if (blockIdx.x * WIDE2_CHAINS >= f.n_peaks || it >= f.n_iters) return;
+    const double *__restrict__ pin = ((it & 1) ? st.pb : st.pa) + 3 * f.off;
+    const int q = blockIdx.z;
+    const double *__restrict__ ox = q == 0 ? st.ox1 : (q == 1 ? st.ox2 : st.ox3);
+    const int c = threadIdx.x % WIDE2_CHAINS, role = threadIdx.x / WIDE2_CHAINS;   // role 0: accumulator
+    const int k = blockIdx.x * WIDE2_CHAINS + c;
+    const bool active = k < f.n_peaks;
+    const long long g = f.off + (active ? k : 0);
+    const int P = f.n_peaks;
+    const int n_tiles = (P + WIDE2_TILE - 1) / WIDE2_TILE;
+    // named barriers 1, 2: full[0], full[1]; 3, 4: empty[0], empty[1]; every use counts all threads
+    auto bar_sync = [](int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(WIDE2_THREADS) : "memory"); };
+    auto bar_arrive = [](int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(WIDE2_THREADS) : "memory"); };
+    if (role == 0) {
+        double acc = 0.0;
+        for (int t = 0; t < n_tiles; ++t) {
+            const int b = t & 1, cnt = min(WIDE2_TILE, P - t * WIDE2_TILE);
+            bar_sync(1 + b);                                          // tile t is in buffer b
+            const double *src = quot + ((size_t)b * WIDE2_TILE) * WIDE2_CHAINS + c;
+            int jj = 0;
+            for (; jj + 8 <= cnt; jj += 8) {
+                double v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = src[(size_t)(jj + u) * WIDE2_CHAINS];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) acc = __dadd_rn(acc, v[u]);
+            }
+            for (; jj < cnt; ++jj) acc = __dadd_rn(acc, src[(size_t)jj * WIDE2_CHAINS]);
+            bar_arrive(3 + b);                                        // buffer b may be refilled
+        }
+        if (active) {
+            const double *__restrict__ oy = q == 0 ? st.oy1 : (q == 1 ? st.oy2 : st.oy3);
+            const double *__restrict__ sy = q == 0 ? st.sy1 : (q == 1 ? st.sy2 : st.sy3);
+            yn[(long long)q * yn_stride + g] = __dmul_rn(sy[g], __ddiv_rn(oy[g], acc));  // :42-54
+        }
+    } else {
+        const int ph = role - 1;
+        const double x = ox[g];
+        const bool x_ok = x_fast_domain(x);
+        for (int t = 0; t < n_tiles; ++t) {
+            const int b = t & 1;
+            if (t >= 2) bar_sync(3 + b);                              // the accumulators are done with tile t-2
+            const int j0 = t * WIDE2_TILE + ph * 8;                   // this thread's 8 Lorentzians
+            double *dst = quot + ((size_t)b * WIDE2_TILE + ph * 8) * WIDE2_CHAINS + c;
+            if (j0 + 8 <= P) {
+                double prm[24];
+#pragma unroll
+                for (int i = 0; i < 24; ++i) prm[i] = __ldg(pin + 3 * j0 + i);
+                bool ok = x_ok;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) ok = ok && params_fast_domain(prm[3 * u], prm[3 * u + 1], prm[3 * u + 2]);
+                double qv[8];
+                if (ok) {
+                    lorentz_multi_q<8>(prm, x, qv);
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {  // unrolled: prm / qv stay in registers
+                        const double d0 = __dsub_rn(x, prm[3 * u + 2]);
+                        qv[u] = __ddiv_rn(prm[3 * u], __dadd_rn(prm[3 * u + 1], __dmul_rn(d0, d0)));
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) dst[(size_t)u * WIDE2_CHAINS] = qv[u];
+            } else {
+                for (int u = 0; j0 + u < P; ++u) {                    // the ragged end: one at a time, IEEE division
+                    const double a = __ldg(pin + 3 * (j0 + u)), h = __ldg(pin + 3 * (j0 + u) + 1), m = __ldg(pin + 3 * (j0 + u) + 2);
+                    const double d0 = __dsub_rn(x, m);
+                    dst[(size_t)u * WIDE2_CHAINS] = __ddiv_rn(a, __dadd_rn(h, __dmul_rn(d0, d0)));
+                }
+            }
+            bar_arrive(1 + b);
+        }
+        // the accumulators' last arrivals on empty[] need their partners
+        for (int t = max(0, n_tiles - 2); t < n_tiles; ++t) bar_sync(3 + (t & 1));
+    }
+}
+
 // grid (ceil(max_peaks / FIT_THREADS), spectra)
 __global__ void __launch_bounds__(FIT_THREADS)
 fit_wide_solve_kernel(const FitDesc *__restrict__ fd, FitState st, const double *__restrict__ yn, long long yn_stride, int it)

@@ -480,10 +480,14 @@ def test_fit_wide_and_per_peak_forms_agree(blood_arrays, monkeypatch):
     x, y = blood_arrays
     r = O.deconvolute_spectrum(O.Settings(ignore_regions=[(4.7, 4.9)]), x, y, (11.8, -2.2))
     want, wtr = O.fit_lorentzian(x, y, r.peaks, 4, trace=True)
-    wide, tr_wide = gpu_fit(x, y, r.peaks, 4)
+    wide, tr_wide = gpu_fit(x, y, r.peaks, 4)          # producers / accumulators (fit_wide2_superpose_kernel)
+    monkeypatch.setenv("MDB_FIT_WIDE", "1")            # 8 Lorentzians per thread (fit_wide_superpose_kernel)
+    ilp, tr_ilp = gpu_fit(x, y, r.peaks, 4)
     monkeypatch.setenv("MDB_FIT_WIDE", "0")
     narrow, tr_narrow = gpu_fit(x, y, r.peaks, 4)
     monkeypatch.delenv("MDB_FIT_WIDE")
+    assert_bit_equal(tr_ilp, wtr, "wide form (instruction-parallel), trace")
+    assert_bit_equal(ilp, want, "wide form (instruction-parallel), retained")
     assert_bit_equal(tr_wide, wtr, "wide form, trace")
     assert_bit_equal(tr_narrow, wtr, "per-peak form, trace")
     assert_bit_equal(wide, want, "wide form, retained")
@@ -498,6 +502,14 @@ def test_fit_wide_and_per_peak_forms_agree(blood_arrays, monkeypatch):
     got, tr = gpu_fit(xs, ys, peaks, 3)
     nan = np.isnan(wtr)
     assert_bit_equal(np.where(nan, 0.0, tr), np.where(nan, 0.0, wtr), "wide form, out-of-domain values")
+    # peak counts around the 56-Lorentzian tile and the 64-chain CTA of the producer form
+    xb, yb = blood_arrays
+    for count in (1, 7, 8, 9, 55, 56, 57, 63, 64, 65, 112, 113, 129):
+        sub = r.peaks[100:100 + count]
+        want_c, wtr_c = O.fit_lorentzian(xb, yb, sub, 2, trace=True)
+        got_c, tr_c = gpu_fit(xb, yb, sub, 2)
+        assert_bit_equal(tr_c, wtr_c, f"wide form, {count} peaks, trace")
+        assert_bit_equal(got_c, want_c, f"wide form, {count} peaks")
 
 
 def test_fit_many_peaks_tiles():
