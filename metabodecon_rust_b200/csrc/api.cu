@@ -1013,7 +1013,11 @@ static mdb_status stage_b(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
             dim3 grid3(grid.x, grid.y, 3);
             // MDB_FIT_WIDE=1 selects the instruction-parallel form (8 Lorentzians per thread), anything else
             // the thread-parallel one (producers / accumulators)
-            const bool wide2 = !(wide_env && wide_env[0] == '1');
+            // (its 512-thread, 57 KB CTAs pay off while they all fit the GPU at once: one blood spectrum is 48
+            // of them; sixteen spectra are 768, and the 128-thread instruction-parallel form is faster again)
+            long long wide2_ctas = 0;
+            for (size_t s = 0; s < S; ++s) wide2_ctas += 3ll * ((ck.fdesc[s].n_peaks + WIDE2_CHAINS - 1) / WIDE2_CHAINS);
+            const bool wide2 = !(wide_env && wide_env[0] == '1') && wide2_ctas <= 2ll * sm_count();
             if (wide2)
                 CUDA_TRY(cudaFuncSetAttribute(fit_wide2_superpose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WIDE2_SMEM));
             for (int it = 0; it < iters; ++it) {
