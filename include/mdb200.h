@@ -113,6 +113,23 @@ int mdb_device_count(void);
  * between them (the in-process form of deconvoluter.rs:699-710's rayon-over-spectra).  The
  * environment variable MDB_DEVICES ("all" or a number) overrides it. */
 mdb_status mdb_set_device_count(int n);
+/* Arithmetic of the two superposition kernels that do NOT feed back into the fit: the full-grid
+ * superposition behind Deconvolution::mse (deconvoluter.rs:540-543, 828-862) and
+ * Lorentzian::superposition_vec / par_superposition_vec (lorentzian.rs:631-663).
+ *   MDB_SUPERPOSITION_EXACT  every operator of the reference replayed with one IEEE rounding each:
+ *                            values and MSE carry the reference's bit patterns;
+ *   MDB_SUPERPOSITION_FAST   (default) 6 instead of 12 FP64 instructions per evaluation (fused
+ *                            denominator, reciprocal to 2^-53 + 2^-60, fused accumulate): each term
+ *                            within about 2 ulp, same summation order; values and MSE agree with the
+ *                            exact mode to about 1e-15 relative (contract: 1e-9).
+ * Peak sets and Lorentzian parameters are bit-identical in both modes (the refinement always uses
+ * exact arithmetic), and so is the choice made by mdb_deconvoluter_optimize_settings, which
+ * compares MSEs and therefore always computes them exactly.  Calls of spectra with at most 4 096
+ * points (one fused launch) are exact in both modes.  Process-wide; the environment variable
+ * MDB_SUPERPOSITION ("exact" | "fast") sets the initial value. */
+enum { MDB_SUPERPOSITION_EXACT = 0, MDB_SUPERPOSITION_FAST = 1 };
+mdb_status mdb_set_superposition_mode(int mode);
+int mdb_superposition_mode(void);
 /* Page-locked host memory for callers that want full-rate H2D (optional helper). */
 mdb_status mdb_host_alloc(void **ptr, size_t bytes);
 mdb_status mdb_host_free(void *ptr);

@@ -69,6 +69,8 @@ SIGNATURES = [
     ("mdb_last_error_message", C.c_char_p, []),
     ("mdb_device_count", C.c_int, []),
     ("mdb_set_device_count", C.c_int, [C.c_int]),
+    ("mdb_set_superposition_mode", C.c_int, [C.c_int]),
+    ("mdb_superposition_mode", C.c_int, []),
     ("mdb_host_alloc", C.c_int, [C.POINTER(_P), C.c_size_t]),
     ("mdb_host_free", C.c_int, [_P]),
     ("mdb_release_workspaces", C.c_int, []),

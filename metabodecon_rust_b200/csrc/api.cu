@@ -254,6 +254,7 @@ struct mdb_deconvoluter {
     mdb_fitting_settings fitting;
     bool has_ignore;
     std::vector<std::pair<double, double>> ignore;
+    bool exact_mse = false;  // internal: optimize_settings compares MSEs, so it always takes the bit-exact K7
 };
 
 extern "C" mdb_status mdb_deconvoluter_new(const mdb_smoothing_settings *sm, const mdb_selection_settings *se,
@@ -1100,7 +1101,9 @@ static mdb_status stage_b(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
         dim3 grid((unsigned)((ck.max_seg_len + per_block - 1) / per_block), (unsigned)n_seg);
         if (grid.x > 0) {
             prof_begin(&ck.spans, MDB_KERNEL_MSE_SUPERPOSITION, ws.stream);
-            auto kern = r == 8 ? superposition_kernel<1, 8> : superposition_kernel<1, 2>;
+            const bool ulp = !dc.exact_mse && mdb_superposition_mode() == MDB_SUPERPOSITION_FAST;
+            auto kern = ulp ? (r == 8 ? superposition_kernel<1, 8, 2> : superposition_kernel<1, 2, 2>)
+                            : (r == 8 ? superposition_kernel<1, 8, 1> : superposition_kernel<1, 2, 1>);
             kern<<<grid, SUP_THREADS, LOR_SMEM_BYTES, ws.stream>>>(nullptr, 0, nullptr, 0, ws.resid.as<double>(), d_desc, d_fd,
                                                                   ws.segs.as<Segment>(), ws.lor.as<double>(),
                                                                   ws.n_kept.as<int>());
@@ -1487,6 +1490,37 @@ static mdb_status run_small(const mdb_deconvoluter &dc, const std::vector<HostSp
 // ---------------------------------------------------------------------------------------------
 // In-process multi-GPU sharding (host-memory batches only)
 // ---------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------
+// Arithmetic of K7 (the MSE superposition) and K8 (superposition_vec); the fit is always exact.
+// ---------------------------------------------------------------------------------------------
+static int initial_superposition_mode()
+{
+    const char *env = std::getenv("MDB_SUPERPOSITION");
+    if (env && std::strcmp(env, "exact") == 0) return MDB_SUPERPOSITION_EXACT;
+    if (env && std::strcmp(env, "fast") == 0) return MDB_SUPERPOSITION_FAST;
+    return MDB_SUPERPOSITION_FAST;
+}
+static std::atomic<int> g_superposition_mode{-1};
+
+extern "C" int mdb_superposition_mode(void)
+{
+    int m = g_superposition_mode.load();
+    if (m < 0) {
+        m = initial_superposition_mode();
+        int expected = -1;
+        if (!g_superposition_mode.compare_exchange_strong(expected, m)) m = expected;
+    }
+    return m;
+}
+
+extern "C" mdb_status mdb_set_superposition_mode(int mode)
+{
+    if (mode != MDB_SUPERPOSITION_EXACT && mode != MDB_SUPERPOSITION_FAST)
+        return fail(MDB_ERR_INVALID_ARGUMENT, "mdb_set_superposition_mode: unknown mode");
+    g_superposition_mode.store(mode);
+    return MDB_OK;
+}
+
 static std::atomic<int> g_device_policy{1};  // 1 = the calling thread's current device; 0 = all visible; n = first n
 
 extern "C" mdb_status mdb_set_device_count(int n)
@@ -1683,6 +1717,7 @@ extern "C" mdb_status mdb_deconvoluter_optimize_settings(mdb_deconvoluter *d, co
                 for (int fit = 5; fit <= 15; fit += 5)
                     variants.push_back({iterations, w, 5.0 + (double)c * (8.0 - 5.0) / 9.0, fit});
     mdb_deconvoluter work = *d;
+    work.exact_mse = true;
     work.selection.kind = MDB_SELECTION_NOISE_SCORE_FILTER;
     work.selection.scoring_method = MDB_SCORING_MINIMUM_SUM;
     work.smoothing.kind = MDB_SMOOTHING_MOVING_AVERAGE;
@@ -1749,7 +1784,9 @@ extern "C" mdb_status mdb_superposition_vec(const double *x, size_t n, const mdb
     if (blocks > 0x7fffffffull) return fail(MDB_ERR_INVALID_ARGUMENT, "grid too large");
     std::vector<ProfSpan> spans;
     prof_begin(&spans, MDB_KERNEL_SUPERPOSITION_VEC, ws->stream);
-    auto kern = r == 8 ? superposition_kernel<0, 8> : superposition_kernel<0, 2>;
+    const bool ulp = mdb_superposition_mode() == MDB_SUPERPOSITION_FAST;
+    auto kern = ulp ? (r == 8 ? superposition_kernel<0, 8, 2> : superposition_kernel<0, 2, 2>)
+                    : (r == 8 ? superposition_kernel<0, 8, 1> : superposition_kernel<0, 2, 1>);
     kern<<<(unsigned)blocks, SUP_THREADS, LOR_SMEM_BYTES, ws->stream>>>(dx, (long long)n, dl, (int)p, dout, nullptr, nullptr,
                                                                       nullptr, nullptr, nullptr);
     LAUNCH_CHECK();

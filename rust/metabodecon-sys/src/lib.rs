@@ -88,6 +88,8 @@ extern "C" {
     pub fn mdb_last_error_message() -> *const c_char;
     pub fn mdb_device_count() -> c_int;
     pub fn mdb_set_device_count(n: c_int) -> mdb_status;
+    pub fn mdb_set_superposition_mode(mode: c_int) -> mdb_status;
+    pub fn mdb_superposition_mode() -> c_int;
     pub fn mdb_host_alloc(ptr: *mut *mut c_void, bytes: usize) -> mdb_status;
     pub fn mdb_host_free(ptr: *mut c_void) -> mdb_status;
     pub fn mdb_release_workspaces() -> mdb_status;

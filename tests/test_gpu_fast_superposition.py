@@ -1,0 +1,221 @@
+"""The library's DEFAULT arithmetic for the two superposition kernels that do not feed back into
+the fit -- K7 (the full-grid superposition behind Deconvolution.mse, deconvoluter.rs:540-543,
+828-862) and K8 (Lorentzian::superposition_vec / par_superposition_vec, lorentzian.rs:631-663):
+MDB_SUPERPOSITION_FAST, 6 instead of 12 FP64 instructions per evaluation (kernels.cuh,
+lorentz_step_ulp).
+
+Bar (BASELINE.json north_star): peak sets bit-exact; Lorentzian parameters and superposition values
+within 1e-9 relative.  What is asserted here, against the CPU oracle on the same inputs:
+  * peak sets and Lorentzian parameters: identical bit patterns (the refinement is always exact);
+  * superposition values: TOL_VALUES = 1e-13 relative (measured: a few 1e-16);
+  * mean squared error: TOL_MSE = 1e-9 relative, the north-star figure (measured: <= 1e-13 on every
+    case here); the residual (S - y) can cancel, so its relative error is not bounded by that of S
+    for a perfect fit -- there the absolute error is checked against the size of S instead;
+  * operands outside the division's fast domain take the IEEE loop in both modes: bit-exact;
+  * optimize_settings picks the same settings (it always computes its MSEs exactly).
+tests/test_gpu_parity.py runs the same kernels in MDB_SUPERPOSITION_EXACT and asserts bits.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import oracle as O
+import synth
+from metabodecon_rust_b200 import Deconvoluter, Spectrum, _lib, set_superposition_mode, superposition_mode
+from metabodecon_rust_b200.lorentzian import superposition_vec_array
+
+pytestmark = pytest.mark.gpu
+
+TOL_VALUES = 1e-13
+TOL_MSE = 1e-9
+
+
+@pytest.fixture(autouse=True)
+def default_mode():
+    set_superposition_mode("fast")
+    yield
+    set_superposition_mode("fast")
+
+
+def rel_err(got, want):
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    return float(np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-300))) if want.size else 0.0
+
+
+def random_lorentzians(rng, p, lo=0.0, hi=10.0):
+    hw = np.exp(rng.uniform(np.log(5e-4), np.log(3e-3), p))
+    sf = np.exp(rng.uniform(np.log(1.0), np.log(1e4), p))
+    return np.stack([sf * hw, hw * hw, rng.uniform(lo, hi, p)], axis=1)
+
+
+def test_fast_is_the_default_and_the_switch_works():
+    assert superposition_mode() == "fast"
+    rng = np.random.default_rng(5)
+    x = np.linspace(-2.2, 11.8, 4099)
+    lor = random_lorentzians(rng, 700)
+    want = O.superposition_vec(x, lor)
+    fast = superposition_vec_array(x, lor)
+    set_superposition_mode("exact")
+    assert superposition_mode() == "exact"
+    exact = superposition_vec_array(x, lor)
+    assert np.array_equal(exact.view(np.uint64), want.view(np.uint64))
+    assert rel_err(fast, want) <= TOL_VALUES
+    with pytest.raises(ValueError):
+        set_superposition_mode("sloppy")
+    assert _lib.load().mdb_set_superposition_mode(7) != 0
+
+
+@pytest.mark.parametrize("n,p", [(1, 1), (31, 3), (1024, 512), (1025, 513), (4097, 1023), (300000, 1100), (2 ** 20 + 5, 40)])
+def test_superposition_vec_within_tolerance_of_oracle(n, p):
+    rng = np.random.default_rng(n * 7 + p)
+    x = np.linspace(-2.2, 11.8, n) if n > 1 else np.array([3.3])
+    lor = random_lorentzians(rng, p)
+    got = superposition_vec_array(x, lor)
+    want = O.superposition_vec(x, lor, parallel=n > 100000)
+    err = rel_err(got, want)
+    assert err <= TOL_VALUES, f"n={n} p={p}: max relative error {err:.3e} > {TOL_VALUES}"
+
+
+def test_superposition_vec_points_on_and_next_to_the_maxima():
+    # x == maxp exactly (denominator = hw2), one grid step away, and far tails (1e6 half widths)
+    rng = np.random.default_rng(11)
+    lor = random_lorentzians(rng, 257)
+    x = np.concatenate([lor[:, 2], lor[:, 2] + np.sqrt(lor[:, 1]), lor[:, 2] + 1e6 * np.sqrt(lor[:, 1]),
+                        np.nextafter(lor[:, 2], np.inf)])
+    err = rel_err(superposition_vec_array(x, lor), O.superposition_vec(x, lor))
+    assert err <= TOL_VALUES, f"{err:.3e}"
+
+
+def test_wide_dynamic_range_inside_the_fast_domain():
+    # parameters spread over 2^-280 .. 2^280 (the fast domain is 2^-300 .. 2^300): every term is still a
+    # normal-number division; terms of one sign, so the sum cannot cancel
+    rng = np.random.default_rng(12)
+    p = 600
+    e = rng.uniform(-280, 280, p)
+    lor = np.stack([np.exp2(e), np.exp2(rng.uniform(-280, 280, p)), rng.uniform(-5, 5, p) * np.exp2(rng.uniform(-100, 100, p))], axis=1)
+    x = rng.uniform(-5, 5, 3000) * np.exp2(rng.uniform(-100, 100, 3000))
+    want = O.superposition_vec(x, lor)
+    got = superposition_vec_array(x, lor)
+    fin = np.isfinite(want)
+    assert fin.any() and np.array_equal(np.isfinite(got), fin)
+    assert rel_err(got[fin], want[fin]) <= TOL_VALUES
+
+
+def test_out_of_domain_operands_take_the_ieee_loop_bit_exactly():
+    # zeros, denormals, infinities, NaN, hw2 = 0 at x = maxp (division by zero): the per-tile domain
+    # check sends these tiles through __ddiv_rn in both modes
+    x = np.array([0.0, 1.0, -1.0, 1e-310, 1e300, np.inf, 2.5])
+    specials = np.array([[1.0, 0.0, 2.5], [0.0, 1.0, 0.0], [1e-320, 1e-320, 0.0], [1.0, 1e-310, 1.0],
+                         [np.inf, 1.0, 0.0], [1.0, np.inf, 0.0], [np.nan, 1.0, 0.0], [1.0, 1.0, np.nan],
+                         [1e308, 1e-308, 1e308], [-1.0, 1.0, 0.5], [1.0, -1.0, 0.5]])
+    for k in range(len(specials)):
+        got = superposition_vec_array(x, specials[k:k + 1])
+        want = O.superposition_vec(x, specials[k:k + 1])
+        both_nan = np.isnan(got) & np.isnan(want)
+        assert np.array_equal(np.where(both_nan, 0.0, got).view(np.uint64), np.where(both_nan, 0.0, want).view(np.uint64)), f"special {k}"
+    # |x| beyond 2^300 leaves the domain through the grid, not the parameters
+    lor = random_lorentzians(np.random.default_rng(3), 40)
+    xs = np.array([1e95, -1e95, 3e200, 1.0])
+    got, want = superposition_vec_array(xs, lor), O.superposition_vec(xs, lor)
+    assert np.array_equal(got.view(np.uint64), want.view(np.uint64))
+
+
+def _check_default_mode(dec, osettings, spectra, what):
+    outs = dec.deconvolute_spectra(spectra)
+    worst = 0.0
+    for i, (sp, out) in enumerate(zip(spectra, outs)):
+        r = O.deconvolute_spectrum(osettings, sp.chemical_shifts, sp.intensities, sp.signal_boundaries)
+        assert r.status == O.OK
+        assert np.array_equal(out.peaks.astype(np.int64), r.peaks.astype(np.int64)), f"{what}[{i}]: peak set differs"
+        got = np.ascontiguousarray(out.parameters, dtype=np.float64)
+        assert np.array_equal(got.view(np.uint64), np.ascontiguousarray(r.lorentzians).view(np.uint64)), f"{what}[{i}]: lorentzians differ in bits"
+        err = abs(out.mse - r.mse) / abs(r.mse)
+        assert err <= TOL_MSE, f"{what}[{i}]: mse {out.mse!r} vs {r.mse!r}, relative error {err:.3e} > {TOL_MSE}"
+        worst = max(worst, err)
+    return outs, worst
+
+
+def test_config1_blood_default_mode(golden_dir):
+    sp = Spectrum.read_bruker(os.path.join(golden_dir, "bruker", "blood_01"), 10, 10, (-2.2, 11.8))
+    dec = Deconvoluter()
+    dec.add_ignore_region((4.7, 4.9))
+    outs, worst = _check_default_mode(dec, O.Settings(ignore_regions=[(4.7, 4.9)]), [sp], "blood_01 water ignored")
+    assert len(outs[0].lorentzians) == 760
+    assert abs(outs[0].mse - float.fromhex("0x1.0808a64fe177ep+35")) <= 1e-12 * 35438015103.04588
+    assert worst <= 1e-12
+    dec.clear_ignore_regions()
+    _check_default_mode(dec, O.Settings(), [sp, sp, sp], "blood_01 x3")
+
+
+def test_config2_jcampdx_default_mode(golden_dir):
+    sp = Spectrum.read_jcampdx(os.path.join(golden_dir, "jcampdx", "blood_01.dx"), (-2.2, 11.8))
+    _check_default_mode(Deconvoluter(), O.Settings(), [sp], "blood_01.dx")
+
+
+def test_synthetic_batches_default_mode():
+    # config-3 and config-5 style spectra (raw and integer-rounded), long enough to leave the fused
+    # small-spectrum path, in one batch spanning R = 8 and R = 2 launches of K7
+    specs = []
+    for s, (n, integer) in enumerate([(32768, False), (16384, True), (65536, False), (20000, True), (8192, False)]):
+        x = synth.axis(n)
+        specs.append(Spectrum(x, synth.config3(40 + s, n=n, integer=integer, x=x), (-2.2, 11.8)))
+    _, worst = _check_default_mode(Deconvoluter(), O.Settings(), specs, "synthetic default")
+    assert worst <= 1e-12
+    dec = Deconvoluter()
+    dec.set_moving_average_smoother(2, 5)
+    dec.set_noise_score_selector(6.5)
+    dec.set_analytical_fitter(5)
+    dec.add_ignore_region((4.7, 4.9))
+    _check_default_mode(dec, O.Settings(smoothing_iterations=2, smoothing_window=5, threshold=6.5, fitting_iterations=5,
+                                        ignore_regions=[(4.7, 4.9)]), specs, "synthetic custom")
+
+
+def test_full_size_batch_default_vs_exact_mode():
+    # 24 config-5 spectra of 2^17 points: the two modes give the same peaks and Lorentzians in bits
+    # and MSEs within TOL_MSE (the oracle is checked on two of them; it needs seconds per spectrum)
+    n = 131072
+    x = synth.axis(n)
+    specs = [Spectrum(x, synth.config5(900 + s, n=n, x=x), (-2.2, 11.8)) for s in range(24)]
+    dec = Deconvoluter()
+    fast = dec.deconvolute_spectra(specs)
+    set_superposition_mode("exact")
+    exact = dec.deconvolute_spectra(specs)
+    set_superposition_mode("fast")
+    for i, (a, b) in enumerate(zip(fast, exact)):
+        assert np.array_equal(a.peaks, b.peaks)
+        assert np.array_equal(np.ascontiguousarray(a.parameters).view(np.uint64), np.ascontiguousarray(b.parameters).view(np.uint64))
+        assert abs(a.mse - b.mse) <= 1e-12 * abs(b.mse), f"[{i}] {a.mse!r} vs {b.mse!r}"
+    _check_default_mode(dec, O.Settings(), specs[:2], "config5 full size")
+
+
+def test_exact_fit_small_residuals():
+    # a noiseless spectrum of well separated Lorentzians is fitted almost exactly: S - y cancels, so
+    # the MSE's relative error is not bounded by that of S; its absolute error is, by 2 * |r| * dS
+    n = 16384
+    x = np.linspace(0.0, 10.0, n)
+    true = np.stack([np.full(8, 2e-3) * 1e5, np.full(8, 4e-6), np.linspace(1.0, 9.0, 8)], axis=1)
+    y = O.superposition_vec(x, true)
+    sp = Spectrum(x, y, (0.5, 9.5))
+    dec = Deconvoluter()
+    dec.set_identity_smoother()
+    dec.set_detector_only()
+    r = O.deconvolute_spectrum(O.Settings(smoothing_kind=O.SMOOTH_IDENTITY, selection_kind=O.SELECT_DETECTOR_ONLY),
+                               x, y, sp.signal_boundaries)
+    if r.status != O.OK:
+        pytest.skip("oracle rejects this construction")
+    out = dec.deconvolute_spectra([sp])[0]
+    assert np.array_equal(np.ascontiguousarray(out.parameters).view(np.uint64), np.ascontiguousarray(r.lorentzians).view(np.uint64))
+    rms, smax = np.sqrt(max(r.mse, 0.0)), float(np.max(np.abs(y)))
+    assert abs(out.mse - r.mse) <= 2.0 * (rms + 1e-13 * smax) * 1e-13 * smax + 1e-9 * r.mse
+
+
+def test_optimize_settings_choice_does_not_depend_on_the_mode(golden_dir):
+    sp = Spectrum.read_bruker(os.path.join(golden_dir, "bruker", "sim_01"), 10, 10, (3.35, 3.55))
+    a, b = Deconvoluter(), Deconvoluter()
+    mse_fast = a.optimize_settings(sp)
+    set_superposition_mode("exact")
+    mse_exact = b.optimize_settings(sp)
+    assert mse_fast == mse_exact  # computed exactly in both modes
+    assert a.smoothing_settings() == b.smoothing_settings() and a.selection_settings() == b.selection_settings()
+    assert a.fitting_settings() == b.fitting_settings()

@@ -20,6 +20,20 @@ pytestmark = pytest.mark.gpu
 REL_TOL = 1e-9  # north_star tolerance for f64 parameters / superposition values
 
 
+@pytest.fixture(autouse=True)
+def exact_superposition(monkeypatch):
+    """This file asserts identical bit patterns everywhere, so it runs the MSE superposition and
+    superposition_vec in MDB_SUPERPOSITION_EXACT.  The library's default (the few-ulp form of those
+    two kernels; peak sets and Lorentzians are bit-identical in both) is covered against the same
+    oracle, with the tolerance written out, in tests/test_gpu_fast_superposition.py."""
+    lib = _lib.load()
+    before = lib.mdb_superposition_mode()
+    monkeypatch.setenv("MDB_SUPERPOSITION", "exact")  # host programs started by a test
+    assert lib.mdb_set_superposition_mode(0) == 0
+    yield
+    assert lib.mdb_set_superposition_mode(before) == 0
+
+
 def bits(a):
     return np.ascontiguousarray(a, dtype=np.float64).view(np.uint64)
 
