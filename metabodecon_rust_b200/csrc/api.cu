@@ -1096,13 +1096,14 @@ static mdb_status stage_b(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
         // R = 8 points per thread is the throughput shape; small batches use R = 2 to fill the SMs
         long long blocks8 = 0;
         for (const Segment &sg : ck.segs) blocks8 += (sg.end - sg.start + SUP_THREADS * 8 - 1) / (SUP_THREADS * 8);
-        const int r = blocks8 >= 2 * sm_count() ? 8 : 2;
+        const bool ulp = !dc.exact_mse && mdb_superposition_mode() == MDB_SUPERPOSITION_FAST;
+        // the few-ulp form runs best with 16 points per thread (tools/kbench.cu, KBENCH_ULP=1) once that fills the GPU
+        const int r = (ulp && blocks8 >= 8 * sm_count() && !std::getenv("MDB_SUP_R8")) ? 16 : blocks8 >= 2 * sm_count() ? 8 : 2;
         const int per_block = SUP_THREADS * r;
         dim3 grid((unsigned)((ck.max_seg_len + per_block - 1) / per_block), (unsigned)n_seg);
         if (grid.x > 0) {
             prof_begin(&ck.spans, MDB_KERNEL_MSE_SUPERPOSITION, ws.stream);
-            const bool ulp = !dc.exact_mse && mdb_superposition_mode() == MDB_SUPERPOSITION_FAST;
-            auto kern = ulp ? (r == 8 ? superposition_kernel<1, 8, 2> : superposition_kernel<1, 2, 2>)
+            auto kern = ulp ? (r == 16 ? superposition_kernel<1, 16, 2> : r == 8 ? superposition_kernel<1, 8, 2> : superposition_kernel<1, 2, 2>)
                             : (r == 8 ? superposition_kernel<1, 8, 1> : superposition_kernel<1, 2, 1>);
             kern<<<grid, SUP_THREADS, LOR_SMEM_BYTES, ws.stream>>>(nullptr, 0, nullptr, 0, ws.resid.as<double>(), d_desc, d_fd,
                                                                   ws.segs.as<Segment>(), ws.lor.as<double>(),
@@ -1778,14 +1779,14 @@ extern "C" mdb_status mdb_superposition_vec(const double *x, size_t n, const mdb
         dl = ws->lor.as<double>();
     }
     const size_t blocks8 = (n + (size_t)SUP_THREADS * 8 - 1) / ((size_t)SUP_THREADS * 8);
-    const int r = blocks8 >= (size_t)2 * sm_count() ? 8 : 2;
+    const bool ulp = mdb_superposition_mode() == MDB_SUPERPOSITION_FAST;
+    const int r = (ulp && blocks8 >= (size_t)8 * sm_count() && !std::getenv("MDB_SUP_R8")) ? 16 : blocks8 >= (size_t)2 * sm_count() ? 8 : 2;
     const size_t per_block = (size_t)SUP_THREADS * r;
     const size_t blocks = (n + per_block - 1) / per_block;
     if (blocks > 0x7fffffffull) return fail(MDB_ERR_INVALID_ARGUMENT, "grid too large");
     std::vector<ProfSpan> spans;
     prof_begin(&spans, MDB_KERNEL_SUPERPOSITION_VEC, ws->stream);
-    const bool ulp = mdb_superposition_mode() == MDB_SUPERPOSITION_FAST;
-    auto kern = ulp ? (r == 8 ? superposition_kernel<0, 8, 2> : superposition_kernel<0, 2, 2>)
+    auto kern = ulp ? (r == 16 ? superposition_kernel<0, 16, 2> : r == 8 ? superposition_kernel<0, 8, 2> : superposition_kernel<0, 2, 2>)
                     : (r == 8 ? superposition_kernel<0, 8, 1> : superposition_kernel<0, 2, 1>);
     kern<<<(unsigned)blocks, SUP_THREADS, LOR_SMEM_BYTES, ws->stream>>>(dx, (long long)n, dl, (int)p, dout, nullptr, nullptr,
                                                                       nullptr, nullptr, nullptr);

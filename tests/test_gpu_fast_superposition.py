@@ -66,7 +66,7 @@ def test_fast_is_the_default_and_the_switch_works():
     assert _lib.load().mdb_set_superposition_mode(7) != 0
 
 
-@pytest.mark.parametrize("n,p", [(1, 1), (31, 3), (1024, 512), (1025, 513), (4097, 1023), (300000, 1100), (2 ** 20 + 5, 40)])
+@pytest.mark.parametrize("n,p", [(1, 1), (31, 3), (1024, 512), (1025, 513), (4097, 1023), (300000, 1100), (2 ** 21 + 5, 40)])  # the last one takes 16 points per thread
 def test_superposition_vec_within_tolerance_of_oracle(n, p):
     rng = np.random.default_rng(n * 7 + p)
     x = np.linspace(-2.2, 11.8, n) if n > 1 else np.array([3.3])
