@@ -31,6 +31,8 @@ pub const MDB_SCORING_MINIMUM_SUM: i32 = 0;
 pub const MDB_FITTING_ANALYTICAL: i32 = 0;
 pub const MDB_MEM_HOST: c_int = 0;
 pub const MDB_MEM_DEVICE: c_int = 1;
+pub const MDB_SUPERPOSITION_EXACT: c_int = 0;
+pub const MDB_SUPERPOSITION_FAST: c_int = 1;
 
 /// `Lorentzian {sfhw, hw2, maxp}` (metabodecon/src/deconvolution/lorentzian.rs:138-145).
 #[repr(C)]
