@@ -189,6 +189,22 @@ def test_full_size_batch_default_vs_exact_mode():
     _check_default_mode(dec, O.Settings(), specs[:2], "config5 full size")
 
 
+def test_sixteen_points_per_thread_with_two_ranges_per_spectrum(golden_dir):
+    # 16 copies of blood_01 with the water region ignored: two MSE ranges per spectrum whose lengths
+    # are no multiple of the 2 048 points a CTA of the 16-points-per-thread K7 covers
+    sp = Spectrum.read_bruker(os.path.join(golden_dir, "bruker", "blood_01"), 10, 10, (-2.2, 11.8))
+    dec = Deconvoluter()
+    dec.add_ignore_region((4.7, 4.9))
+    fast = dec.deconvolute_spectra([sp] * 16)
+    set_superposition_mode("exact")
+    exact = dec.deconvolute_spectra([sp] * 16)
+    set_superposition_mode("fast")
+    assert float(exact[0].mse).hex() == "0x1.0808a64fe177ep+35"
+    for a, b in zip(fast, exact):
+        assert np.array_equal(np.ascontiguousarray(a.parameters).view(np.uint64), np.ascontiguousarray(b.parameters).view(np.uint64))
+        assert a.mse == fast[0].mse and abs(a.mse - b.mse) <= 1e-12 * b.mse
+
+
 def test_exact_fit_small_residuals():
     # a noiseless spectrum of well separated Lorentzians is fitted almost exactly: S - y cancels, so
     # the MSE's relative error is not bounded by that of S; its absolute error is, by 2 * |r| * dS

@@ -32,5 +32,8 @@ rng = np.random.default_rng(1)
 lor = np.stack([rng.uniform(1e-3, 1.0, 777), rng.uniform(1e-7, 1e-5, 777), rng.uniform(0, 10, 777)], axis=1)
 lor[5] = [0.0, 1e-6, 5.0]  # leaves the fast-division domain: IEEE tile
 print("superposition", float(superposition_vec_array(np.linspace(-2, 12, 10001), lor).sum()))
+# the few-ulp form with 16 points per thread (default mode, grids of at least 1 184 x 1 024 points)
+big = superposition_vec_array(np.linspace(-2, 12, 1184 * 1024 + 77), lor[:40])
+print("superposition, 16 points per thread", float(big[::4099].sum()))
 sim = Spectrum.read_bruker(os.path.join(ROOT, "tests", "golden", "bruker", "sim_01"), 10, 10, (3.339, 3.553))
 print("optimize", Deconvoluter().optimize_settings(sim))
