@@ -205,6 +205,52 @@ def test_sixteen_points_per_thread_with_two_ranges_per_spectrum(golden_dir):
         assert a.mse == fast[0].mse and abs(a.mse - b.mse) <= 1e-12 * b.mse
 
 
+def test_randomised_differential_default_mode(monkeypatch):
+    """60 random spectra (integer / float values, flat stretches, 200..6000 points) under random
+    settings, in random-size batches, through the GENERAL pipeline (the fused small-spectrum kernel is
+    exact in both modes, so it is switched off here): statuses, peak sets and Lorentzians as the
+    oracle's in bits, MSE within TOL_MSE."""
+    from test_oracle_kats import _random_spectrum
+    monkeypatch.setenv("MDB_SMALL_PATH", "0")
+    rng = np.random.default_rng(4242)
+    done, worst = 0, 0.0
+    while done < 60:
+        batch = int(rng.integers(1, 9))
+        iters, window = int(rng.integers(1, 6)), int(rng.choice([2, 3, 4, 5, 7, 9, 11]))
+        thr, fit = float(rng.uniform(0.5, 8.0)), int(rng.integers(1, 12))
+        dec = Deconvoluter()
+        dec.set_moving_average_smoother(iters, window)
+        dec.set_noise_score_selector(thr)
+        dec.set_analytical_fitter(fit)
+        settings = O.Settings(smoothing_iterations=iters, smoothing_window=window, threshold=thr, fitting_iterations=fit)
+        specs, wants = [], []
+        for _ in range(batch):
+            n = int(rng.integers(200, 6000))
+            x, y = _random_spectrum(rng, n)
+            sb = (float(rng.uniform(7.0, 9.5)), float(rng.uniform(-1.5, 1.0)))
+            sp = Spectrum(x, y, sb)
+            specs.append(sp)
+            wants.append(O.deconvolute_spectrum(settings, x, y, sp.signal_boundaries))
+        done += batch
+        if any(w.status != O.OK for w in wants):
+            with pytest.raises(Exception):
+                dec.deconvolute_spectra(specs)
+            continue
+        for i, (out, w) in enumerate(zip(dec.deconvolute_spectra(specs), wants)):
+            what = f"random case {done - batch + i} (iters={iters}, window={window}, thr={thr:.3f}, fit={fit})"
+            assert np.array_equal(out.peaks.astype(np.int64), w.peaks.astype(np.int64)), what
+            nan = np.isnan(w.lorentzians)
+            got = np.where(nan, 0.0, np.ascontiguousarray(out.parameters, dtype=np.float64))
+            assert np.array_equal(got.view(np.uint64), np.where(nan, 0.0, w.lorentzians).view(np.uint64)), what
+            if np.isnan(w.mse) or np.isinf(w.mse):
+                assert (np.isnan(out.mse) and np.isnan(w.mse)) or out.mse == w.mse, what
+            else:
+                err = abs(out.mse - w.mse) / abs(w.mse) if w.mse != 0.0 else abs(out.mse)
+                assert err <= TOL_MSE, f"{what}: mse {out.mse!r} vs {w.mse!r} ({err:.3e})"
+                worst = max(worst, err)
+    assert worst <= TOL_MSE
+
+
 def test_exact_fit_small_residuals():
     # a noiseless spectrum of well separated Lorentzians is fitted almost exactly: S - y cancels, so
     # the MSE's relative error is not bounded by that of S; its absolute error is, by 2 * |r| * dS
