@@ -50,7 +50,7 @@ int main(int argc, char **argv)
 
     /* Peak sets and Lorentzians are the reference's bit patterns in either mode; the MSE and
      * superposition values are too under MDB_SUPERPOSITION=exact (or
-     * mdb_set_superposition_mode(MDB_SUPERPOSITION_EXACT)), and within about 1e-15 relative of them
+     * mdb_set_superposition_mode(MDB_SUPERPOSITION_EXACT)), and within about 1e-15 (MSE: 1e-13) relative of them
      * in the default mode. */
     mdb_deconvoluter *dec = NULL;
     mdb_deconvoluter_default(&dec);

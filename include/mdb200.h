@@ -120,8 +120,10 @@ mdb_status mdb_set_device_count(int n);
  *                            values and MSE carry the reference's bit patterns;
  *   MDB_SUPERPOSITION_FAST   (default) 6 instead of 12 FP64 instructions per evaluation (fused
  *                            denominator, reciprocal to 2^-53 + 2^-60, fused accumulate): each term
- *                            within about 2 ulp, same summation order; values and MSE agree with the
- *                            exact mode to about 1e-15 relative (contract: 1e-9).
+ *                            within about 2 ulp, same summation order over the Lorentzians; the
+ *                            squared residuals of the MSE are summed by a fixed tree instead of one
+ *                            left fold.  Superposition values agree with the exact mode to about
+ *                            1e-15 relative, the MSE to about 1e-13 (contract: 1e-9).
  * Peak sets and Lorentzian parameters are bit-identical in both modes (the refinement always uses
  * exact arithmetic), and so is the choice made by mdb_deconvoluter_optimize_settings, which
  * compares MSEs and therefore always computes them exactly.  Calls of spectra with at most 4 096

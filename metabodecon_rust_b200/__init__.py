@@ -24,7 +24,7 @@ def set_devices(n: int) -> None:
 def set_superposition_mode(mode: str) -> None:
     """Arithmetic of the MSE superposition and of `Lorentzian.superposition_vec`: "exact" replays the
     reference's operators bit for bit; "fast" (default) halves the FP64 instructions per evaluation
-    and agrees to about 1e-15 relative.  Peak sets and Lorentzian parameters are identical in both."""
+    and agrees to about 1e-15 relative (1e-13 for the MSE).  Peak sets and Lorentzian parameters are identical in both."""
     from . import _lib
     from .exceptions import raise_for_status
     modes = {"exact": 0, "fast": 1}

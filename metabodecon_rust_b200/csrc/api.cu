@@ -1112,7 +1112,11 @@ static mdb_status stage_b(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
             prof_end(&ck.spans, ws.stream, -1.0);  // work = sum(points * kept), known in finish_chunk
         }
         prof_begin(&ck.spans, MDB_KERNEL_MSE_REDUCE, ws.stream);
-        mse_reduce_kernel<<<(unsigned)((S + MSE_WARPS - 1) / MSE_WARPS), 32 * MSE_WARPS, 0, ws.stream>>>(d_fd, ws.segs.as<Segment>(),
+        if (ulp)  // default mode: CTA-wide tree per range instead of the ordered fold (mse_reduce_fast_kernel)
+            mse_reduce_fast_kernel<<<(unsigned)S, MSE_FAST_THREADS, 0, ws.stream>>>(d_fd, ws.segs.as<Segment>(), ws.resid.as<double>(),
+                                                                                ws.mse.as<double>(), (int)S);
+        else
+            mse_reduce_kernel<<<(unsigned)((S + MSE_WARPS - 1) / MSE_WARPS), 32 * MSE_WARPS, 0, ws.stream>>>(d_fd, ws.segs.as<Segment>(),
                                                                                   ws.resid.as<double>(), ws.mse.as<double>(), (int)S);
         LAUNCH_CHECK();
         prof_end(&ck.spans, ws.stream, 8.0 * (double)ck.res_total);

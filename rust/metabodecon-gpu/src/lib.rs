@@ -201,7 +201,7 @@ pub fn superposition_vec(x: &[f64], lorentzians: &[Lorentzian]) -> Result<Vec<f6
 
 /// Arithmetic of `Deconvolution::mse` and `superposition_vec` (include/mdb200.h,
 /// `mdb_set_superposition_mode`): `true` replays the reference's operators bit for bit, `false`
-/// (the library default) uses half the FP64 instructions and agrees to about 1e-15 relative.
+/// (the library default) uses half the FP64 instructions and agrees to about 1e-15 relative (1e-13 for the MSE).
 /// Peak sets and Lorentzian parameters are bit-identical in both.
 pub fn set_exact_superposition(exact: bool) -> Result<()> {
     check(unsafe {

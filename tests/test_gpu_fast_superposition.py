@@ -8,8 +8,8 @@ Bar (BASELINE.json north_star): peak sets bit-exact; Lorentzian parameters and s
 within 1e-9 relative.  What is asserted here, against the CPU oracle on the same inputs:
   * peak sets and Lorentzian parameters: identical bit patterns (the refinement is always exact);
   * superposition values: TOL_VALUES = 1e-13 relative (measured: a few 1e-16);
-  * mean squared error: TOL_MSE = 1e-9 relative, the north-star figure (measured: <= 1e-13 on every
-    case here); the residual (S - y) can cancel, so its relative error is not bounded by that of S
+  * mean squared error (few-ulp terms, residuals summed by a fixed tree instead of a left fold):
+    TOL_MSE = 1e-9 relative, the north-star figure (measured: a few 1e-14 on every case here); the residual (S - y) can cancel, so its relative error is not bounded by that of S
     for a perfect fit -- there the absolute error is checked against the size of S instead;
   * operands outside the division's fast domain take the IEEE loop in both modes: bit-exact;
   * optimize_settings picks the same settings (it always computes its MSEs exactly).
