@@ -126,8 +126,7 @@ mdb_status mdb_set_device_count(int n);
  *                            1e-15 relative, the MSE to about 1e-13 (contract: 1e-9).
  * Peak sets and Lorentzian parameters are bit-identical in both modes (the refinement always uses
  * exact arithmetic), and so is the choice made by mdb_deconvoluter_optimize_settings, which
- * compares MSEs and therefore always computes them exactly.  Calls of spectra with at most 4 096
- * points (one fused launch) are exact in both modes.  Process-wide; the environment variable
+ * compares MSEs and therefore always computes them exactly.  Process-wide; the environment variable
  * MDB_SUPERPOSITION ("exact" | "fast") sets the initial value. */
 enum { MDB_SUPERPOSITION_EXACT = 0, MDB_SUPERPOSITION_FAST = 1 };
 mdb_status mdb_set_superposition_mode(int mode);

@@ -1454,7 +1454,8 @@ static mdb_status run_small(const mdb_deconvoluter &dc, const std::vector<HostSp
         prof_begin(&spans, MDB_KERNEL_SMALL_FUSED, ws.stream);
         small_fused_kernel<<<(unsigned)S, SMALL_THREADS, smem, ws.stream>>>(
             d_desc, reinterpret_cast<const SmallDesc *>(db + off_small), n_al, dc.selection.kind,
-            smooth_fused ? (int)dc.smoothing.iterations : 0, (int)dc.smoothing.window_size, d_stamps);
+            smooth_fused ? (int)dc.smoothing.iterations : 0, (int)dc.smoothing.window_size,
+            (!dc.exact_mse && mdb_superposition_mode() == MDB_SUPERPOSITION_FAST) ? 1 : 0, d_stamps);
         LAUNCH_CHECK();
         prof_end(&spans, ws.stream, (double)S);
         CUDA_TRY(cudaStreamSynchronize(ws.stream));

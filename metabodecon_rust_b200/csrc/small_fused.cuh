@@ -149,7 +149,8 @@ __device__ __forceinline__ void lorentz_multi(const double *p, const double x, d
 
 // Squared residuals of R points per thread, points i0 + t + r * SMALL_THREADS below e0
 // (deconvoluter.rs:846-855): ordered superposition of the kept Lorentzians, minus y, squared.
-template <int R>
+// ULP: the few-ulp evaluation of MDB_SUPERPOSITION_FAST (lorentz_step_ulp) inside the fast domain.
+template <int R, bool ULP>
 __device__ __forceinline__ void small_mse_block(const double *__restrict__ x, const double *__restrict__ y, const double *kept,
                                                 int n_kept, bool kfast, int i0, int e0, double *resid)
 {
@@ -166,10 +167,10 @@ __device__ __forceinline__ void small_mse_block(const double *__restrict__ x, co
     if (idx[0] >= e0) return;
     if (kfast && xok) {
 #pragma unroll 2
-        for (int j = 0; j < n_kept; ++j) lorentz_step<R, true>(kept[3 * j], kept[3 * j + 1], kept[3 * j + 2], xv, acc);
+        for (int j = 0; j < n_kept; ++j) lorentz_step<R, ULP ? 2 : 1>(kept[3 * j], kept[3 * j + 1], kept[3 * j + 2], xv, acc);
     } else {
 #pragma unroll 1
-        for (int j = 0; j < n_kept; ++j) lorentz_step<R, false>(kept[3 * j], kept[3 * j + 1], kept[3 * j + 2], xv, acc);
+        for (int j = 0; j < n_kept; ++j) lorentz_step<R, 0>(kept[3 * j], kept[3 * j + 1], kept[3 * j + 2], xv, acc);
     }
 #pragma unroll
     for (int r = 0; r < R; ++r)
@@ -337,7 +338,7 @@ __device__ __forceinline__ void small_smooth_warp(double *rows, int row_stride, 
 
 __global__ void __launch_bounds__(SMALL_THREADS)
 small_fused_kernel(const SpecDesc *__restrict__ sd, const SmallDesc *__restrict__ xd, int n_al, int selector_kind,
-                   int smooth_iters, int smooth_window, long long *__restrict__ stamps)
+                   int smooth_iters, int smooth_window, int fast_mse, long long *__restrict__ stamps)
 {
     // optional phase clock of CTA 0 (MDB_SMALL_STAMPS=1, development aid): SM cycles at phase ends
     int stamp_k = 0;
@@ -346,6 +347,7 @@ small_fused_kernel(const SpecDesc *__restrict__ sd, const SmallDesc *__restrict_
     extern __shared__ __align__(16) unsigned char small_smem[];
     __shared__ int warp_cnt[SMALL_WARPS];
     __shared__ __align__(16) double smooth_sink[SMALL_SMOOTH_U];
+    __shared__ double mse_part[SMALL_WARPS];
     __shared__ int s_raw, s_np, s_c0, s_c1;
     __shared__ double s_thr, s_mean, s_sd;
 
@@ -632,25 +634,57 @@ small_fused_kernel(const SpecDesc *__restrict__ sd, const SmallDesc *__restrict_
     bool kok = true;
     for (int k = t; k < n_kept; k += SMALL_THREADS) kok = kok && params_fast_domain(kept[3 * k], kept[3 * k + 1], kept[3 * k + 2]);
     const bool kfast = __syncthreads_and(kok);
-    {
+    auto mse_ranges = [&](auto ulp) {
+        constexpr bool ULP = decltype(ulp)::value;
         int pos = 0;
         for (int q = 0; q < e.n_ranges; ++q) {
             const int s0 = e.ranges[2 * q], e0 = e.ranges[2 * q + 1];
             int i0 = s0;
             for (; e0 - i0 >= SMALL_THREADS * SMALL_R; i0 += SMALL_THREADS * SMALL_R)
-                small_mse_block<SMALL_R>(d.x, d.y, kept, n_kept, kfast, i0, e0, resid + pos - s0);
+                small_mse_block<SMALL_R, ULP>(d.x, d.y, kept, n_kept, kfast, i0, e0, resid + pos - s0);
             // the rest of the range with just enough points per thread (no thread evaluates padding)
             const int rest = (e0 - i0 + SMALL_THREADS - 1) / SMALL_THREADS;
-            if (rest == 4) small_mse_block<4>(d.x, d.y, kept, n_kept, kfast, i0, e0, resid + pos - s0);
-            else if (rest == 3) small_mse_block<3>(d.x, d.y, kept, n_kept, kfast, i0, e0, resid + pos - s0);
-            else if (rest == 2) small_mse_block<2>(d.x, d.y, kept, n_kept, kfast, i0, e0, resid + pos - s0);
-            else if (rest == 1) small_mse_block<1>(d.x, d.y, kept, n_kept, kfast, i0, e0, resid + pos - s0);
+            if (rest == 4) small_mse_block<4, ULP>(d.x, d.y, kept, n_kept, kfast, i0, e0, resid + pos - s0);
+            else if (rest == 3) small_mse_block<3, ULP>(d.x, d.y, kept, n_kept, kfast, i0, e0, resid + pos - s0);
+            else if (rest == 2) small_mse_block<2, ULP>(d.x, d.y, kept, n_kept, kfast, i0, e0, resid + pos - s0);
+            else if (rest == 1) small_mse_block<1, ULP>(d.x, d.y, kept, n_kept, kfast, i0, e0, resid + pos - s0);
             pos += e0 - s0;
         }
-    }
+    };
+    if (fast_mse) mse_ranges(std::true_type{});
+    else mse_ranges(std::false_type{});
     __syncthreads();
     stamp();  // 7: MSE superposition
-    if (t == 0) {
+    if (fast_mse) {
+        // default mode: every range summed by the whole CTA through a fixed tree (as mse_reduce_fast_kernel),
+        // the range sums folded in range order
+        double residuals = 0.0;
+        long long length = 0;
+        int pos = 0;
+        for (int q = 0; q < e.n_ranges; ++q) {
+            const int len = e.ranges[2 * q + 1] - e.ranges[2 * q];
+            const double *__restrict__ src = resid + pos;
+            double v = 0.0;
+            for (int i = t; i < len; i += SMALL_THREADS) v = __dadd_rn(v, src[i]);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) v = __dadd_rn(v, __shfl_down_sync(0xffffffffu, v, off));
+            if ((t & 31) == 0) mse_part[t >> 5] = v;
+            __syncthreads();
+            if (t == 0) {
+                double part = 0.0;
+#pragma unroll
+                for (int w = 0; w < SMALL_WARPS; ++w) part = __dadd_rn(part, mse_part[w]);
+                residuals = __dadd_rn(residuals, part);
+            }
+            __syncthreads();
+            length += len;
+            pos += len;
+        }
+        if (t == 0) {
+            o.mse = __ddiv_rn(residuals, (double)length);
+            *hdr = o;
+        }
+    } else if (t == 0) {
         // each range is a left fold from 0.0, the range sums are folded in range order (:846-861)
         double residuals = 0.0;
         long long length = 0;

@@ -207,8 +207,8 @@ def test_sixteen_points_per_thread_with_two_ranges_per_spectrum(golden_dir):
 
 def test_randomised_differential_default_mode(monkeypatch):
     """60 random spectra (integer / float values, flat stretches, 200..6000 points) under random
-    settings, in random-size batches, through the GENERAL pipeline (the fused small-spectrum kernel is
-    exact in both modes, so it is switched off here): statuses, peak sets and Lorentzians as the
+    settings, in random-size batches, through the GENERAL pipeline (the fused small-spectrum kernel has
+    its own test above, so it is switched off here): statuses, peak sets and Lorentzians as the
     oracle's in bits, MSE within TOL_MSE."""
     from test_oracle_kats import _random_spectrum
     monkeypatch.setenv("MDB_SMALL_PATH", "0")
@@ -249,6 +249,38 @@ def test_randomised_differential_default_mode(monkeypatch):
                 assert err <= TOL_MSE, f"{what}: mse {out.mse!r} vs {w.mse!r} ({err:.3e})"
                 worst = max(worst, err)
     assert worst <= TOL_MSE
+
+
+def test_small_spectrum_path_default_mode(monkeypatch, golden_dir):
+    # spectra of up to 4 096 points take the one-launch fused kernel, whose MSE tail follows the mode
+    # too (few-ulp superposition, tree-summed residuals): against the oracle, and against the general
+    # pipeline in the same mode
+    lib = _lib.load()
+    sim = Spectrum.read_bruker(os.path.join(golden_dir, "bruker", "sim_01"), 10, 10, (3.35, 3.55))
+    specs = [sim]
+    for s, n in enumerate([2048, 3001, 4096, 700]):
+        x = synth.axis(n)
+        specs.append(Spectrum(x, synth.spectrum(5000 + s, n=n, k=25, hw_range=(8e-3, 5e-2), x=x), (-2.2, 11.8)))
+    dec = Deconvoluter()
+    lib.mdb_reset_kernel_launch_count()
+    outs, worst = _check_default_mode(dec, O.Settings(), specs, "small path")
+    assert worst <= 1e-12
+    dec.add_ignore_region((4.7, 4.9))  # two MSE ranges in the synthetic ones
+    small, _ = _check_default_mode(dec, O.Settings(ignore_regions=[(4.7, 4.9)]), specs[1:], "small path, ignore region")
+    lib.mdb_reset_kernel_launch_count()
+    dec.deconvolute_spectra(specs[1:])
+    assert lib.mdb_kernel_launch_count() == 1
+    monkeypatch.setenv("MDB_SMALL_PATH", "0")
+    general = dec.deconvolute_spectra(specs[1:])
+    for a, b in zip(small, general):
+        assert np.array_equal(np.ascontiguousarray(a.parameters).view(np.uint64), np.ascontiguousarray(b.parameters).view(np.uint64))
+        assert abs(a.mse - b.mse) <= 1e-12 * abs(b.mse)
+    monkeypatch.delenv("MDB_SMALL_PATH")
+    set_superposition_mode("exact")
+    exact = dec.deconvolute_spectra(specs[1:])
+    for sp, out in zip(specs[1:], exact):
+        r = O.deconvolute_spectrum(O.Settings(ignore_regions=[(4.7, 4.9)]), sp.chemical_shifts, sp.intensities, sp.signal_boundaries)
+        assert out.mse == r.mse
 
 
 def test_exact_fit_small_residuals():
