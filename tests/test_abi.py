@@ -189,6 +189,22 @@ def test_compute_fails_loudly_without_a_device():
         Lorentzian.superposition_vec(x, [Lorentzian(1.0, 1.0, 0.0)])
 
 
+def test_superposition_mode_switch_is_host_logic():
+    # include/mdb200.h: process-wide, needs no device; FAST is the default, unknown values are refused
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r); import metabodecon_rust_b200 as m; from metabodecon_rust_b200 import _lib; "
+            "print(m.superposition_mode()); m.set_superposition_mode('exact'); print(m.superposition_mode()); "
+            "print(_lib.load().mdb_set_superposition_mode(9) != 0); print(m.superposition_mode())") % ROOT
+    for env_value, first in ((None, "fast"), ("exact", "exact"), ("fast", "fast")):
+        env = dict(os.environ)
+        env.pop("MDB_SUPERPOSITION", None)
+        if env_value:
+            env["MDB_SUPERPOSITION"] = env_value
+        out = subprocess.run([sys.executable, "-c", code], env=env, check=True, capture_output=True, text=True).stdout.split()
+        assert out == [first, "exact", "True", "exact"], out
+
+
 def test_product_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "metabodecon_rust_b200")
     for base, _, files in os.walk(pkg):
