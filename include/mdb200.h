@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MDB200_ABI_VERSION 1
+#define MDB200_ABI_VERSION 2
 
 /* ---------------------------------------------------------------------------------------------
  * Status codes.  1..7 mirror deconvolution::error::Kind (deconvolution/error.rs:39-95),
@@ -110,7 +110,8 @@ int mdb_device_count(void);
 /* GPUs used by ONE mdb_deconvolute_spectra call on host-memory batches: 1 (default) = the calling
  * thread's current device; 0 = every visible device; n = CUDA devices 0..n-1.  With more than one,
  * the batch is cut into contiguous shards, one host thread and one pipeline per GPU, no exchange
- * between them (the in-process form of deconvoluter.rs:699-710's rayon-over-spectra).  The
+ * between them (the in-process form of deconvoluter.rs:699-710's rayon-over-spectra); host-memory
+ * mdb_superposition_vec calls cut their grid the same way (lorentzian.rs:656-663).  The
  * environment variable MDB_DEVICES ("all" or a number) overrides it. */
 mdb_status mdb_set_device_count(int n);
 /* Arithmetic of the two superposition kernels that do NOT feed back into the fit: the full-grid
@@ -118,19 +119,31 @@ mdb_status mdb_set_device_count(int n);
  * Lorentzian::superposition_vec / par_superposition_vec (lorentzian.rs:631-663).
  *   MDB_SUPERPOSITION_EXACT  every operator of the reference replayed with one IEEE rounding each:
  *                            values and MSE carry the reference's bit patterns;
- *   MDB_SUPERPOSITION_FAST   (default) 6 instead of 12 FP64 instructions per evaluation (fused
- *                            denominator, reciprocal to 2^-53 + 2^-60, fused accumulate): each term
- *                            within about 2 ulp, same summation order over the Lorentzians; the
- *                            squared residuals of the MSE are summed by a fixed tree instead of one
- *                            left fold.  Superposition values agree with the exact mode to about
- *                            1e-15 relative, the MSE to about 1e-13 (contract: 1e-9).
+ *   MDB_SUPERPOSITION_FAST   6 instead of 12 FP64 instructions per evaluation (fused denominator,
+ *                            reciprocal to 2^-53 + 2^-60, fused accumulate): each term within about
+ *                            2 ulp, same summation order over the Lorentzians; the squared residuals
+ *                            of the MSE are summed by a fixed tree instead of one left fold.
+ *                            Superposition values agree with the exact mode to about 1e-15
+ *                            relative, the MSE to about 1e-13 (contract: 1e-9).
  * Peak sets and Lorentzian parameters are bit-identical in both modes (the refinement always uses
  * exact arithmetic), and so is the choice made by mdb_deconvoluter_optimize_settings, which
- * compares MSEs and therefore always computes them exactly.  Process-wide; the environment variable
- * MDB_SUPERPOSITION ("exact" | "fast") sets the initial value. */
+ * compares MSEs and therefore always computes them exactly.
+ *
+ * The mode is PER DECONVOLUTER (mdb_deconvoluter_set_superposition_mode pins it) and an explicit
+ * argument of mdb_superposition_vec_mode: two deconvoluters of one process may differ and run
+ * concurrently.  mdb_set_superposition_mode only sets the process DEFAULT -- what a deconvoluter that
+ * was never pinned uses (read once at the start of each call) and what the argument-less
+ * mdb_superposition_vec uses.  Its initial value is MDB_SUPERPOSITION_FAST unless the environment
+ * variable MDB_SUPERPOSITION says "exact" or "fast"; any other value makes the calls that need the
+ * default fail with MDB_ERR_INVALID_ARGUMENT (never a silent fallback).  mdb_superposition_mode
+ * returns the default (negative when the environment variable is malformed). */
 enum { MDB_SUPERPOSITION_EXACT = 0, MDB_SUPERPOSITION_FAST = 1 };
 mdb_status mdb_set_superposition_mode(int mode);
 int mdb_superposition_mode(void);
+/* FP64 instruction rate of the current device, measured: independent DFMA / DADD streams on every
+ * SM for a few milliseconds, CUDA events on the launching stream.  Instructions (not flops) per
+ * second; the denominator bench.py's fp64_pipe_util is quoted against. */
+mdb_status mdb_measure_fp64_rate(double *dfma_per_s, double *dadd_per_s);
 /* Page-locked host memory for callers that want full-rate H2D (optional helper). */
 mdb_status mdb_host_alloc(void **ptr, size_t bytes);
 mdb_status mdb_host_free(void *ptr);
@@ -201,6 +214,27 @@ mdb_status mdb_deconvoluter_set_fitting_settings(mdb_deconvoluter *d, const mdb_
 /* add_ignore_region / clear_ignore_regions  deconvoluter.rs:438-492 (sort + merge included) */
 mdb_status mdb_deconvoluter_add_ignore_region(mdb_deconvoluter *d, double lo, double hi);
 void mdb_deconvoluter_clear_ignore_regions(mdb_deconvoluter *d);
+/* Pins the arithmetic of the MSE superposition of THIS deconvoluter (MDB_SUPERPOSITION_*); clones
+ * inherit it.  The getter returns the pinned mode, or the process default for a deconvoluter that was
+ * never pinned.  No counterpart in the reference (which has one arithmetic); see the enum above. */
+mdb_status mdb_deconvoluter_set_superposition_mode(mdb_deconvoluter *d, int mode);
+int mdb_deconvoluter_superposition_mode(const mdb_deconvoluter *d);
+/* Arithmetic of the refinement passes (fitter_analytical.rs:39-66).  MDB_FIT_EXACT (default, the
+ * product): the reference's operators, one IEEE rounding each -- Lorentzian parameters carry the
+ * reference's bit patterns.  The other two are OPT-IN experiments whose measured deviation is
+ * recorded in DESIGN.md section 2:
+ *   MDB_FIT_CORRECTED  the division keeps its Markstein correction but drops the second Newton step
+ *                      of the reciprocal (10 instead of 12 FP64 instructions per evaluation); the
+ *                      quotient is the correctly rounded one except when a/b lies within ~2^-103
+ *                      of a rounding boundary (about one quotient in 2^49);
+ *   MDB_FIT_ULP        the 6-instruction few-ulp evaluation of MDB_SUPERPOSITION_FAST inside the
+ *                      refinement: parameters drift by far more than 1e-9 relative on real spectra
+ *                      (the analytic solve amplifies ulp noise).
+ * The environment variable MDB_FIT_ARITHMETIC ("exact" | "corrected" | "ulp") sets the initial value
+ * of new deconvoluters. */
+enum { MDB_FIT_EXACT = 0, MDB_FIT_CORRECTED = 1, MDB_FIT_ULP = 2 };
+mdb_status mdb_deconvoluter_set_fit_arithmetic(mdb_deconvoluter *d, int kind);
+int mdb_deconvoluter_fit_arithmetic(const mdb_deconvoluter *d);
 
 /* ---------------------------------------------------------------------------------------------
  * Deconvolution results (deconvolution/deconvolution.rs:45-56).  A batch result owns S
@@ -261,6 +295,13 @@ mdb_status mdb_deconvoluter_optimize_settings(mdb_deconvoluter *d, const mdb_spe
  */
 mdb_status mdb_superposition_vec(const double *x, size_t n, const mdb_lorentzian *lorentzians,
                                  size_t n_lorentzians, double *out, int memory);
+/* The same with the arithmetic stated by the caller (MDB_SUPERPOSITION_*) instead of the process
+ * default.  Host-memory calls honour mdb_set_device_count: the grid is cut into contiguous slices,
+ * one per GPU, the parameter table is replicated, and every slice streams through its GPU in
+ * chunks (H2D, kernel and D2H of neighbouring chunks overlap) -- the form of par_superposition_vec's
+ * rayon-over-points (lorentzian.rs:656-663).  Slices are bit-identical to a one-shot evaluation. */
+mdb_status mdb_superposition_vec_mode(const double *x, size_t n, const mdb_lorentzian *lorentzians,
+                                      size_t n_lorentzians, double *out, int memory, int mode);
 
 /* ---------------------------------------------------------------------------------------------
  * Stage entry points.  The reference keeps these behind crate-private traits (Smoother,

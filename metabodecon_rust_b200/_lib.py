@@ -35,6 +35,9 @@ MDB_SELECTION_DETECTOR_ONLY, MDB_SELECTION_NOISE_SCORE_FILTER = 0, 1
 MDB_SCORING_MINIMUM_SUM = 0
 MDB_FITTING_ANALYTICAL = 0
 MDB_MEM_HOST, MDB_MEM_DEVICE = 0, 1
+MDB_SUPERPOSITION_EXACT, MDB_SUPERPOSITION_FAST = 0, 1
+MDB_FIT_EXACT, MDB_FIT_CORRECTED, MDB_FIT_ULP = 0, 1, 2
+ABI_VERSION = 2
 KERNEL_NAMES = ["smooth", "detect", "select", "fit_init", "fit_iter", "retain", "mse_superposition",
                 "mse_reduce", "superposition_vec", "small_fused"]
 
@@ -71,6 +74,7 @@ SIGNATURES = [
     ("mdb_set_device_count", C.c_int, [C.c_int]),
     ("mdb_set_superposition_mode", C.c_int, [C.c_int]),
     ("mdb_superposition_mode", C.c_int, []),
+    ("mdb_measure_fp64_rate", C.c_int, [_DP, _DP]),
     ("mdb_host_alloc", C.c_int, [C.POINTER(_P), C.c_size_t]),
     ("mdb_host_free", C.c_int, [_P]),
     ("mdb_release_workspaces", C.c_int, []),
@@ -95,6 +99,10 @@ SIGNATURES = [
     ("mdb_deconvoluter_set_fitting_settings", C.c_int, [_P, C.POINTER(FittingSettings)]),
     ("mdb_deconvoluter_add_ignore_region", C.c_int, [_P, C.c_double, C.c_double]),
     ("mdb_deconvoluter_clear_ignore_regions", None, [_P]),
+    ("mdb_deconvoluter_set_superposition_mode", C.c_int, [_P, C.c_int]),
+    ("mdb_deconvoluter_superposition_mode", C.c_int, [_P]),
+    ("mdb_deconvoluter_set_fit_arithmetic", C.c_int, [_P, C.c_int]),
+    ("mdb_deconvoluter_fit_arithmetic", C.c_int, [_P]),
     ("mdb_batch_len", C.c_size_t, [_P]),
     ("mdb_batch_status", C.c_int, [_P, C.c_size_t]),
     ("mdb_batch_n_lorentzians", C.c_size_t, [_P, C.c_size_t]),
@@ -108,6 +116,7 @@ SIGNATURES = [
     ("mdb_deconvolute_spectra", C.c_int, [_P, C.POINTER(SpectrumView), C.c_size_t, C.c_int, C.POINTER(_P)]),
     ("mdb_deconvoluter_optimize_settings", C.c_int, [_P, C.POINTER(SpectrumView), C.c_int, _DP]),
     ("mdb_superposition_vec", C.c_int, [_P, C.c_size_t, _P, C.c_size_t, _P, C.c_int]),
+    ("mdb_superposition_vec_mode", C.c_int, [_P, C.c_size_t, _P, C.c_size_t, _P, C.c_int, C.c_int]),
     ("mdb_stage_smooth", C.c_int, [_P, C.c_size_t, C.c_uint64, C.c_uint64, _P]),
     ("mdb_stage_smooth_batch", C.c_int, [_P, C.c_size_t, C.c_size_t, C.c_size_t, C.c_uint64, C.c_uint64, _P, _DP]),
     ("mdb_stage_detect", C.c_int, [_P, C.c_size_t, _P, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
@@ -134,7 +143,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError here means the header and the library disagree
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.mdb_abi_version() != 1:
+    if lib.mdb_abi_version() != ABI_VERSION:
         raise ImportError(f"{LIB_PATH}: unexpected ABI version {lib.mdb_abi_version()}")
     _lib = lib
     return lib

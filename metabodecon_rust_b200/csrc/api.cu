@@ -18,7 +18,9 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <condition_variable>
 #include <cstring>
+#include <deque>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -248,13 +250,61 @@ static mdb_status validate_fitting(const mdb_fitting_settings &s)  // fitter.rs:
     return MDB_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Arithmetic of K7 (the MSE superposition) and K8 (superposition_vec).  The mode is a property of
+// each mdb_deconvoluter (and an explicit argument of mdb_superposition_vec_mode); the process-wide
+// value below is only the DEFAULT a new deconvoluter starts with and what the argument-less
+// mdb_superposition_vec uses.  MDB_SUPERPOSITION ("exact" | "fast") sets its initial value; any
+// other value is an error reported by the first call that needs it -- never a silent fallback.
+// ---------------------------------------------------------------------------------------------
+static std::atomic<int> g_superposition_default{-1};
+
+static int initial_superposition_mode()  // -2: MDB_SUPERPOSITION holds an unknown value
+{
+    const char *env = std::getenv("MDB_SUPERPOSITION");
+    if (!env || !env[0]) return MDB_SUPERPOSITION_FAST;
+    if (std::strcmp(env, "exact") == 0) return MDB_SUPERPOSITION_EXACT;
+    if (std::strcmp(env, "fast") == 0) return MDB_SUPERPOSITION_FAST;
+    return -2;
+}
+
+extern "C" int mdb_superposition_mode(void)
+{
+    int m = g_superposition_default.load();
+    if (m == -1) {
+        m = initial_superposition_mode();
+        int expected = -1;
+        if (!g_superposition_default.compare_exchange_strong(expected, m)) m = expected;
+    }
+    return m;  // -2 when the environment variable is malformed
+}
+
+static mdb_status default_superposition_mode(int *mode)
+{
+    const int m = mdb_superposition_mode();
+    if (m < 0)
+        return fail(MDB_ERR_INVALID_ARGUMENT, std::string("MDB_SUPERPOSITION must be \"exact\" or \"fast\", not \"")
+                                                  + (std::getenv("MDB_SUPERPOSITION") ? std::getenv("MDB_SUPERPOSITION") : "") + "\"");
+    *mode = m;
+    return MDB_OK;
+}
+
+extern "C" mdb_status mdb_set_superposition_mode(int mode)
+{
+    if (mode != MDB_SUPERPOSITION_EXACT && mode != MDB_SUPERPOSITION_FAST)
+        return fail(MDB_ERR_INVALID_ARGUMENT, "mdb_set_superposition_mode: unknown mode");
+    g_superposition_default.store(mode);
+    return MDB_OK;
+}
+
 struct mdb_deconvoluter {
     mdb_smoothing_settings smoothing;
     mdb_selection_settings selection;
     mdb_fitting_settings fitting;
     bool has_ignore;
     std::vector<std::pair<double, double>> ignore;
-    bool exact_mse = false;  // internal: optimize_settings compares MSEs, so it always takes the bit-exact K7
+    int sup_mode = -1;  // arithmetic of K7: -1 = the process default at call time, else pinned (mdb_deconvoluter_set_superposition_mode)
+    int fit_arith = MDB_FIT_EXACT;          // arithmetic of K6; anything but EXACT is an opt-in experiment
 };
 
 extern "C" mdb_status mdb_deconvoluter_new(const mdb_smoothing_settings *sm, const mdb_selection_settings *se,
@@ -266,6 +316,11 @@ extern "C" mdb_status mdb_deconvoluter_new(const mdb_smoothing_settings *sm, con
     if ((st = validate_selection(*se)) != MDB_OK) return st;
     if ((st = validate_fitting(*fi)) != MDB_OK) return st;
     auto *d = new mdb_deconvoluter();
+    if (const char *fa = std::getenv("MDB_FIT_ARITHMETIC")) {  // experiments only; the product default is EXACT
+        if (std::strcmp(fa, "corrected") == 0) d->fit_arith = MDB_FIT_CORRECTED;
+        else if (std::strcmp(fa, "ulp") == 0) d->fit_arith = MDB_FIT_ULP;
+        else if (std::strcmp(fa, "exact") != 0) { delete d; return fail(MDB_ERR_INVALID_ARGUMENT, "MDB_FIT_ARITHMETIC must be exact, corrected or ulp"); }
+    }
     d->smoothing = *sm;
     d->selection = *se;
     d->fitting = *fi;
@@ -292,6 +347,30 @@ extern "C" mdb_status mdb_deconvoluter_clone(const mdb_deconvoluter *src, mdb_de
 }
 
 extern "C" void mdb_deconvoluter_free(mdb_deconvoluter *d) { delete d; }
+
+extern "C" mdb_status mdb_deconvoluter_set_superposition_mode(mdb_deconvoluter *d, int mode)
+{
+    if (!d) return fail(MDB_ERR_INVALID_ARGUMENT, "null argument");
+    if (mode != MDB_SUPERPOSITION_EXACT && mode != MDB_SUPERPOSITION_FAST)
+        return fail(MDB_ERR_INVALID_ARGUMENT, "mdb_deconvoluter_set_superposition_mode: unknown mode");
+    d->sup_mode = mode;
+    return MDB_OK;
+}
+extern "C" int mdb_deconvoluter_superposition_mode(const mdb_deconvoluter *d)
+{
+    if (!d) return -1;
+    return d->sup_mode >= 0 ? d->sup_mode : mdb_superposition_mode();
+}
+
+extern "C" mdb_status mdb_deconvoluter_set_fit_arithmetic(mdb_deconvoluter *d, int kind)
+{
+    if (!d) return fail(MDB_ERR_INVALID_ARGUMENT, "null argument");
+    if (kind != MDB_FIT_EXACT && kind != MDB_FIT_CORRECTED && kind != MDB_FIT_ULP)
+        return fail(MDB_ERR_INVALID_ARGUMENT, "mdb_deconvoluter_set_fit_arithmetic: unknown kind");
+    d->fit_arith = kind;
+    return MDB_OK;
+}
+extern "C" int mdb_deconvoluter_fit_arithmetic(const mdb_deconvoluter *d) { return d ? d->fit_arith : -1; }
 
 extern "C" mdb_status mdb_deconvoluter_smoothing_settings(const mdb_deconvoluter *d, mdb_smoothing_settings *out)
 {
@@ -461,7 +540,13 @@ struct PinBuf {
 
 struct Workspace {
     int device = -1;
-    cudaStream_t stream = nullptr;
+    // Two streams per workspace.  `stream_a` (highest priority) carries stage A -- input copies, K1
+    // smoothing, K2/K3 detection, K4 selection: short, latency- or bandwidth-bound kernels; `stream`
+    // (lowest priority) carries stage B -- the FP64-bound fit and MSE kernels.  Grids of different
+    // chunks are dispatched in priority order as SM slots free up, so the stage-A kernels of the next
+    // chunks slip in beside the long FP64 grids of the current ones instead of queueing behind
+    // them (their CTAs need few registers and little FP64 issue, so they overlap for free).
+    cudaStream_t stream = nullptr, stream_a = nullptr;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     // stage A
     DevBuf x, y, ys, tmp, tile_cnt, pk, sc, sfr, sel, ig, desc, sel_out;
@@ -484,8 +569,9 @@ struct Workspace {
         if (ev_a) cudaEventDestroy(ev_a);
         if (ev_b) cudaEventDestroy(ev_b);
         if (stream) cudaStreamDestroy(stream);
+        if (stream_a) cudaStreamDestroy(stream_a);
         ev_a = ev_b = nullptr;
-        stream = nullptr;
+        stream = stream_a = nullptr;
     }
 };
 
@@ -511,7 +597,11 @@ static mdb_status acquire_workspace(Workspace **out)
     }
     auto *ws = new Workspace();
     ws->device = dev;
-    cudaError_t e = cudaStreamCreateWithFlags(&ws->stream, cudaStreamNonBlocking);
+    int prio_least = 0, prio_greatest = 0;
+    cudaError_t e = cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+    if (const char *env = std::getenv("MDB_STREAM_PRIORITIES")) if (env[0] == '0') prio_greatest = prio_least;  // measurement aid
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ws->stream, cudaStreamNonBlocking, prio_least);
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&ws->stream_a, cudaStreamNonBlocking, prio_greatest);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ws->ev_a, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ws->ev_b, cudaEventDisableTiming);
     if (e != cudaSuccess) {
@@ -526,6 +616,7 @@ static mdb_status acquire_workspace(Workspace **out)
 static void release_workspace(Workspace *ws)
 {
     if (!ws) return;
+    cudaStreamSynchronize(ws->stream_a);  // callers synchronise `stream`; nothing may be pending on either
     std::lock_guard<std::mutex> lock(g_pool_mutex);
     g_pool.emplace(ws->device, ws);
 }
@@ -621,6 +712,86 @@ static void precompute_spec(HostSpec &h, const mdb_deconvoluter &dc)
 }
 
 // ---------------------------------------------------------------------------------------------
+// Pageable host rows (what a drop-in caller holds: Spectrum owns Arc<[f64]>, spectrum/spectrum.rs:
+// 101-116; NumPy arrays from Python): cudaMemcpyAsync would bounce them through the driver's own
+// staging buffer on the calling thread at ~10 GB/s and block it.  Instead a few host threads gather
+// the rows of a chunk into the chunk workspace's page-locked staging area, one chunk AHEAD of the
+// pipeline (the job is submitted when the chunk is created, one iteration before its stage A), in
+// parts of ~32 MB so that the DMA of part p runs while part p+1 is still being gathered.
+// ---------------------------------------------------------------------------------------------
+struct HostSpec;
+struct StageJob {
+    std::vector<const double *> src;     // row pointers
+    std::vector<size_t> len, off;        // elements per row, element offset in the staging area
+    double *dst = nullptr;
+    std::vector<size_t> part_end;        // row index (exclusive) closing each part
+    std::vector<int> part_of_row;
+    std::unique_ptr<std::atomic<int>[]> part_left;  // rows of the part not yet copied
+    std::atomic<size_t> next{0};
+    std::mutex m;
+    std::condition_variable cv;
+    void wait_part(size_t p)
+    {
+        std::unique_lock<std::mutex> lk(m);
+        cv.wait(lk, [&] { return part_left[p].load() == 0; });
+    }
+};
+
+class Stager {
+  public:
+    explicit Stager(size_t n_threads)
+    {
+        for (size_t t = 0; t < n_threads; ++t) threads_.emplace_back([this] { worker(); });
+    }
+    ~Stager()
+    {
+        { std::lock_guard<std::mutex> lk(m_); stop_ = true; }
+        cv_.notify_all();
+        for (auto &t : threads_) t.join();
+    }
+    void submit(const std::shared_ptr<StageJob> &j)
+    {
+        { std::lock_guard<std::mutex> lk(m_); q_.push_back(j); }
+        cv_.notify_all();
+    }
+  private:
+    void worker()
+    {
+        for (;;) {
+            std::shared_ptr<StageJob> j;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return stop_ || !q_.empty(); });
+                if (q_.empty()) return;  // stop requested and nothing left
+                j = q_.front();
+            }
+            const size_t rows = j->src.size();
+            for (;;) {
+                const size_t r = j->next.fetch_add(1);
+                if (r >= rows) break;
+                std::memcpy(j->dst + j->off[r], j->src[r], j->len[r] * 8);
+                if (j->part_left[j->part_of_row[r]].fetch_sub(1) == 1) {
+                    std::lock_guard<std::mutex> lk(j->m);
+                    j->cv.notify_all();
+                }
+            }
+            std::lock_guard<std::mutex> lk(m_);
+            if (!q_.empty() && q_.front() == j) q_.pop_front();  // every row has been claimed
+        }
+    }
+    std::vector<std::thread> threads_;
+    std::deque<std::shared_ptr<StageJob>> q_;
+    std::mutex m_;
+    std::condition_variable cv_;
+    bool stop_ = false;
+};
+
+// Number of pipelines of this process that run side by side (the in-process multi-GPU sharder sets it
+// in its worker threads): the staging threads of one pipeline are sized so that all of them together
+// stay within the host's cores.
+static thread_local int t_pipeline_peers = 1;
+
+// ---------------------------------------------------------------------------------------------
 // The pipeline over one chunk of spectra
 // ---------------------------------------------------------------------------------------------
 struct Chunk {
@@ -634,32 +805,30 @@ struct Chunk {
     int max_tiles = 0, max_peaks = 0, max_seg_len = 0;
     bool stage_b_launched = false, finished = false;
     double est_evals = 0.0;            // Lorentzian evaluations of this chunk's fit + MSE kernels (from the counts)
+    std::shared_ptr<StageJob> stage_job;  // pageable host rows being gathered into ws->h_stage (null: none)
     std::vector<ProfSpan> spans;       // per-kernel timing, resolved in finish_chunk
 };
 
-static int smem_optin_limit()
-{
-    static int lim = -1;
-    if (lim < 0) {
-        int dev = 0, v = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-        lim = v;
-    }
-    return lim;
-}
+// Device attributes used by the launch heuristics, cached PER DEVICE (the in-process sharder runs one
+// host thread per GPU, and callers may sit on any device) behind a once-flag each.
+struct DeviceInfo { std::once_flag once; int smem_optin = 0; int sms = 148; };
+static DeviceInfo g_device_info[64];
 
-static int sm_count()
+static const DeviceInfo &device_info()
 {
-    static int n = -1;
-    if (n < 0) {
-        int dev = 0, v = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
-        n = v > 0 ? v : 148;
-    }
-    return n;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    DeviceInfo &di = g_device_info[(dev >= 0 && dev < 64) ? dev : 0];
+    std::call_once(di.once, [&]() {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) == cudaSuccess) di.smem_optin = v;
+        v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) di.sms = v;
+    });
+    return di;
 }
+static int smem_optin_limit() { return device_info().smem_optin; }
+static int sm_count() { return device_info().sms; }
 
 // K1 dispatch: the lane-per-pass TMA-staged kernel when the settings are covered (window 2..9,
 // up to 32 iterations) and every input row is 16-byte aligned, else one generic pass per launch.
@@ -727,7 +896,9 @@ static mdb_status stage_a(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
     // ---- layout
     size_t y_elems = 0, cand_elems = 0, tile_elems = 0, ig_elems = 0;
     std::vector<size_t> y_off(S), cand_off(S), tile_off(S), ig_off(S);
-    std::map<const double *, size_t> x_map;  // caller x pointer -> element offset in ws.x
+    // (caller x pointer, length) -> element offset in ws.x.  The length is part of the key: two views of
+    // one axis array (big[:1000], big[:2000]) share the pointer but not the row.
+    std::map<std::pair<const double *, size_t>, size_t> x_map;
     size_t x_elems = 0;
     ck.max_tiles = 0;
     for (size_t s = 0; s < S; ++s) {
@@ -742,8 +913,8 @@ static mdb_status stage_a(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
         ig_off[s] = ig_elems;
         ig_elems += h.ig.size();
         ck.max_tiles = std::max(ck.max_tiles, (int)tiles);
-        if (memory == MDB_MEM_HOST && !x_map.count(h.x)) {
-            x_map[h.x] = x_elems;
+        if (memory == MDB_MEM_HOST && !x_map.count({h.x, h.n})) {
+            x_map[{h.x, h.n}] = x_elems;
             x_elems += align_up(h.n, 16);
         }
     }
@@ -775,7 +946,7 @@ static mdb_status stage_a(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
         const HostSpec &h = hs[ck.first + s];
         SpecDesc &d = ck.desc[s];
         if (memory == MDB_MEM_HOST) {
-            d.x = ws.x.as<double>() + x_map[h.x];
+            d.x = ws.x.as<double>() + x_map[{h.x, h.n}];
             d.y = ws.y.as<double>() + y_off[s];
         } else {
             d.x = h.x;
@@ -799,43 +970,36 @@ static mdb_status stage_a(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
         for (size_t q = 0; q < h.ig.size(); ++q) h_ig[ig_off[s] + q] = h.ig[q];
     }
     std::memcpy(ws.h_desc.p, ck.desc.data(), S * sizeof(SpecDesc));
-    CUDA_TRY(counted_memcpy_async(ws.desc.p, ws.h_desc.p, S * sizeof(SpecDesc), cudaMemcpyHostToDevice, ws.stream));
+    CUDA_TRY(counted_memcpy_async(ws.desc.p, ws.h_desc.p, S * sizeof(SpecDesc), cudaMemcpyHostToDevice, ws.stream_a));
     if (ig_elems)
-        CUDA_TRY(counted_memcpy_async(ws.ig.p, ws.h_ig.p, ig_elems * 4, cudaMemcpyHostToDevice, ws.stream));
+        CUDA_TRY(counted_memcpy_async(ws.ig.p, ws.h_ig.p, ig_elems * 4, cudaMemcpyHostToDevice, ws.stream_a));
 
     // ---- inputs to the device (rows that are adjacent on the host and on the device go as one copy)
     double *y_dst = skip_smoothing_input_is_smoothed ? ws.ys.as<double>() : ws.y.as<double>();
     if (memory == MDB_MEM_HOST) {
-        for (auto &kv : x_map) {
-            size_t n = 0;
-            for (size_t s = 0; s < S; ++s)
-                if (hs[ck.first + s].x == kv.first) { n = hs[ck.first + s].n; break; }
-            CUDA_TRY(counted_memcpy_async(ws.x.as<double>() + kv.second, kv.first, n * 8, cudaMemcpyHostToDevice, ws.stream));
-        }
-        if (!host_rows_pinned(hs, ck.first, S)) {
-            // Pageable rows (what NumPy / Vec<f64> callers hand over): the driver would stage them
-            // through its own bounce buffer on this thread at ~10 GB/s.  Gather them instead into
-            // the workspace's pinned staging area with a few host threads (laid out exactly like
-            // ws.y), then one full-rate DMA.
+        for (auto &kv : x_map)
+            CUDA_TRY(counted_memcpy_async(ws.x.as<double>() + kv.second, kv.first.first, kv.first.second * 8,
+                                          cudaMemcpyHostToDevice, ws.stream_a));
+        if (ck.stage_job) {
+            // pageable rows, gathered ahead of time by the staging threads (prepare_staging): one DMA per part
+            StageJob &job = *ck.stage_job;
+            size_t row0 = 0;
+            for (size_t pt = 0; pt < job.part_end.size(); ++pt) {
+                job.wait_part(pt);
+                const size_t row1 = job.part_end[pt];
+                const size_t e0 = y_off[row0], e1 = row1 < S ? y_off[row1] : y_elems;
+                CUDA_TRY(counted_memcpy_async(y_dst + e0, job.dst + e0, (e1 - e0) * 8, cudaMemcpyHostToDevice, ws.stream_a));
+                row0 = row1;
+            }
+            ck.stage_job.reset();
+        } else if (!host_rows_pinned(hs, ck.first, S)) {
+            // pageable rows of a single-chunk entry point (the stage_* functions): gather on this thread
             CUDA_TRY(ws.h_stage.ensure(y_elems * 8));
             double *stage = ws.h_stage.as<double>();
-            CUDA_TRY(cudaStreamSynchronize(ws.stream));  // the previous DMA out of this staging area has finished
-            const unsigned hw = std::max(2u, std::thread::hardware_concurrency());
-            size_t n_thr = std::min<size_t>({(size_t)8, (size_t)hw / 2, S});
-            if (y_elems * 8 < ((size_t)4 << 20)) n_thr = 1;  // small chunks: spawning threads costs more than the copy
-            if (n_thr <= 1) {
-                for (size_t s = 0; s < S; ++s)
-                    std::memcpy(stage + y_off[s], hs[ck.first + s].y, hs[ck.first + s].n * 8);
-            } else {
-                std::vector<std::thread> pool;
-                for (size_t t = 0; t < n_thr; ++t)
-                    pool.emplace_back([&, t]() {
-                        for (size_t s = t; s < S; s += n_thr)
-                            std::memcpy(stage + y_off[s], hs[ck.first + s].y, hs[ck.first + s].n * 8);
-                    });
-                for (auto &th : pool) th.join();
-            }
-            CUDA_TRY(counted_memcpy_async(y_dst, stage, y_elems * 8, cudaMemcpyHostToDevice, ws.stream));
+            CUDA_TRY(cudaStreamSynchronize(ws.stream_a));  // the previous DMA out of this staging area has finished
+            for (size_t s = 0; s < S; ++s)
+                std::memcpy(stage + y_off[s], hs[ck.first + s].y, hs[ck.first + s].n * 8);
+            CUDA_TRY(counted_memcpy_async(y_dst, stage, y_elems * 8, cudaMemcpyHostToDevice, ws.stream_a));
         } else {
             size_t s = 0;
             while (s < S) {
@@ -847,27 +1011,27 @@ static mdb_status stage_a(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
                     if (hp.n % 16 == 0 && hn.y == hp.y + hp.n) { bytes += hn.n * 8; ++e; }
                     else break;
                 }
-                CUDA_TRY(counted_memcpy_async(y_dst + y_off[s], h0.y, bytes, cudaMemcpyHostToDevice, ws.stream));
+                CUDA_TRY(counted_memcpy_async(y_dst + y_off[s], h0.y, bytes, cudaMemcpyHostToDevice, ws.stream_a));
                 s = e;
             }
         }
     } else if (skip_smoothing_input_is_smoothed) {
         for (size_t s = 0; s < S; ++s)
             CUDA_TRY(counted_memcpy_async(y_dst + y_off[s], hs[ck.first + s].y, hs[ck.first + s].n * 8,
-                                     cudaMemcpyDeviceToDevice, ws.stream));
+                                     cudaMemcpyDeviceToDevice, ws.stream_a));
     }
 
     const SpecDesc *d_desc = ws.desc.as<SpecDesc>();
     // ---- K1 smoothing (deconvoluter.rs:531-532)
     if (!skip_smoothing_input_is_smoothed && !preset) {
         if (ma) {
-            mdb_status sst = launch_smooth(ws.stream, d_desc, ck.desc, (int)dc.smoothing.iterations,
+            mdb_status sst = launch_smooth(ws.stream_a, d_desc, ck.desc, (int)dc.smoothing.iterations,
                                            (int)dc.smoothing.window_size, &ck.spans);
             if (sst != MDB_OK) return sst;
         } else {  // Identity (smoothing/identity.rs): the smoothed copy is the input itself
             for (size_t s = 0; s < S; ++s)
                 CUDA_TRY(counted_memcpy_async(ck.desc[s].ys, ck.desc[s].y, (size_t)ck.desc[s].n * 8,
-                                         cudaMemcpyDeviceToDevice, ws.stream));
+                                         cudaMemcpyDeviceToDevice, ws.stream_a));
         }
     }
     // ---- K2/K3 detection + scoring
@@ -875,10 +1039,10 @@ static mdb_status stage_a(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
         dim3 grid((unsigned)((ck.max_tiles + DETECT_WARPS - 1) / DETECT_WARPS), (unsigned)S);
         double pts = 0.0;
         for (size_t s = 0; s < S; ++s) pts += (double)ck.desc[s].n;
-        prof_begin(&ck.spans, MDB_KERNEL_DETECT, ws.stream);
-        detect_kernel<<<grid, DETECT_THREADS, 0, ws.stream>>>(d_desc);
+        prof_begin(&ck.spans, MDB_KERNEL_DETECT, ws.stream_a);
+        detect_kernel<<<grid, DETECT_THREADS, 0, ws.stream_a>>>(d_desc);
         LAUNCH_CHECK();
-        prof_end(&ck.spans, ws.stream, 8.0 * pts);  // algorithmic bytes: read 8N
+        prof_end(&ck.spans, ws.stream_a, 8.0 * pts);  // algorithmic bytes: read 8N
     }
     // ---- K4 selection
     {
@@ -889,13 +1053,13 @@ static mdb_status stage_a(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
         auto kern = few ? select_kernel<1024> : select_kernel<SELECT_THREADS>;
         if (smem > 40 * 1024)
             CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        prof_begin(&ck.spans, MDB_KERNEL_SELECT, ws.stream);
-        kern<<<(unsigned)S, few ? 1024 : SELECT_THREADS, smem, ws.stream>>>(d_desc, ws.sel_out.as<SelectOut>(), dc.selection.kind);
+        prof_begin(&ck.spans, MDB_KERNEL_SELECT, ws.stream_a);
+        kern<<<(unsigned)S, few ? 1024 : SELECT_THREADS, smem, ws.stream_a>>>(d_desc, ws.sel_out.as<SelectOut>(), dc.selection.kind);
         LAUNCH_CHECK();
-        prof_end(&ck.spans, ws.stream, (double)S);
+        prof_end(&ck.spans, ws.stream_a, (double)S);
     }
-    CUDA_TRY(counted_memcpy_async(ws.h_sel_out.p, ws.sel_out.p, S * sizeof(SelectOut), cudaMemcpyDeviceToHost, ws.stream));
-    CUDA_TRY(cudaEventRecord(ws.ev_a, ws.stream));
+    CUDA_TRY(counted_memcpy_async(ws.h_sel_out.p, ws.sel_out.p, S * sizeof(SelectOut), cudaMemcpyDeviceToHost, ws.stream_a));
+    CUDA_TRY(cudaEventRecord(ws.ev_a, ws.stream_a));
     return MDB_OK;
 }
 
@@ -914,7 +1078,6 @@ static void fit_state_pointers(Workspace &ws, long long p_total, FitState &st)
 static mdb_status stage_b(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_deconvoluter &dc,
                           std::vector<SpecResult> &results, bool with_mse, mdb_lorentzian *trace)
 {
-    (void)dc;  // per-spectrum settings travel in HostSpec since optimize_settings
     Workspace &ws = *ck.ws;
     const size_t S = ck.count;
     CUDA_TRY(cudaEventSynchronize(ws.ev_a));
@@ -941,8 +1104,7 @@ static mdb_status stage_b(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
             for (auto &rg : h.ranges) {
                 Segment sg;
                 sg.spec = (int)s; sg.start = rg.first; sg.end = rg.second; sg.pad_ = 0;
-                sg.res_off = ck.res_total;
-                ck.res_total += (long long)align_up((size_t)(rg.second - rg.first), 16);
+                sg.res_off = 0;  // assigned below, once the launch shape of K7 is known
                 ck.max_seg_len = std::max(ck.max_seg_len, rg.second - rg.first);
                 ck.segs.push_back(sg);
                 ++f.seg_cnt;
@@ -958,6 +1120,20 @@ static mdb_status stage_b(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
     }
     const size_t P = (size_t)std::max<long long>(ck.p_total, 1);
     const size_t n_seg = ck.segs.size();
+    // K7 launch shape.  R = 8 points per thread is the throughput shape; small batches use R = 2 to fill
+    // the SMs; the few-ulp form runs best with 16 points per thread (tools/kbench.cu, KBENCH_ULP=1) once
+    // that still fills the GPU.  In the few-ulp mode a CTA hands on ONE sum of squared residuals (MODE 2
+    // of superposition_kernel), so a range owns ceil(len / per_block) slots of `resid` instead of len.
+    const bool ulp = dc.sup_mode == MDB_SUPERPOSITION_FAST;
+    long long blocks8 = 0;
+    for (const Segment &sg : ck.segs) blocks8 += (sg.end - sg.start + SUP_THREADS * 8 - 1) / (SUP_THREADS * 8);
+    const int sup_r = (ulp && blocks8 >= 8 * sm_count() && !std::getenv("MDB_SUP_R8")) ? 16 : blocks8 >= 2 * sm_count() ? 8 : 2;
+    const int per_block = SUP_THREADS * sup_r;
+    for (Segment &sg : ck.segs) {
+        sg.res_off = ck.res_total;
+        const size_t len = (size_t)(sg.end - sg.start);
+        ck.res_total += (long long)(ulp ? (len + per_block - 1) / per_block : align_up(len, 16));
+    }
     CUDA_TRY(ws.fdesc.ensure(S * sizeof(FitDesc)));
     CUDA_TRY(ws.h_fdesc.ensure(S * sizeof(FitDesc)));
     CUDA_TRY(ws.segs.ensure(std::max<size_t>(n_seg, 1) * sizeof(Segment)));
@@ -1007,7 +1183,9 @@ static mdb_status stage_b(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
         long long fit_blocks = 0;
         for (size_t s = 0; s < S; ++s) fit_blocks += (ck.fdesc[s].n_peaks + FIT_THREADS - 1) / FIT_THREADS;
         const char *wide_env = std::getenv("MDB_FIT_WIDE");
-        const bool wide = fit_blocks <= sm_count() && !(wide_env && wide_env[0] == '0') && !(persistent && persistent[0] == '1');
+        // (the opt-in arithmetic experiments exist in the one-thread-per-peak kernel only)
+        const bool wide = fit_blocks <= sm_count() && !(wide_env && wide_env[0] == '0') && !(persistent && persistent[0] == '1')
+                          && dc.fit_arith == MDB_FIT_EXACT;
         if (wide) {
             const long long yn_stride = (long long)align_up(P, 16);
             double *yn = ws.fit_state.as<double>() + 11 * yn_stride;
@@ -1047,7 +1225,8 @@ static mdb_status stage_b(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
                 for (size_t s = 0; s < S; ++s)
                     if (it < ck.fdesc[s].n_iters) evals += 3.0 * (double)ck.fdesc[s].n_peaks * (double)ck.fdesc[s].n_peaks;
                 prof_begin(&ck.spans, MDB_KERNEL_FIT_ITER, ws.stream);
-                fit_iter_kernel<<<grid, FIT_THREADS, LOR_SMEM_BYTES, ws.stream>>>(d_fd, st, it);
+                auto fit_kern = dc.fit_arith == MDB_FIT_ULP ? fit_iter_kernel<2> : dc.fit_arith == MDB_FIT_CORRECTED ? fit_iter_kernel<3> : fit_iter_kernel<1>;
+                fit_kern<<<grid, FIT_THREADS, LOR_SMEM_BYTES, ws.stream>>>(d_fd, st, it);
                 LAUNCH_CHECK();
                 prof_end(&ck.spans, ws.stream, evals);
                 if (trace)
@@ -1093,17 +1272,11 @@ static mdb_status stage_b(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
     LAUNCH_CHECK();
     prof_end(&ck.spans, ws.stream, (double)ck.p_total);
     if (with_mse && n_seg) {
-        // R = 8 points per thread is the throughput shape; small batches use R = 2 to fill the SMs
-        long long blocks8 = 0;
-        for (const Segment &sg : ck.segs) blocks8 += (sg.end - sg.start + SUP_THREADS * 8 - 1) / (SUP_THREADS * 8);
-        const bool ulp = !dc.exact_mse && mdb_superposition_mode() == MDB_SUPERPOSITION_FAST;
-        // the few-ulp form runs best with 16 points per thread (tools/kbench.cu, KBENCH_ULP=1) once that fills the GPU
-        const int r = (ulp && blocks8 >= 8 * sm_count() && !std::getenv("MDB_SUP_R8")) ? 16 : blocks8 >= 2 * sm_count() ? 8 : 2;
-        const int per_block = SUP_THREADS * r;
+        const int r = sup_r;
         dim3 grid((unsigned)((ck.max_seg_len + per_block - 1) / per_block), (unsigned)n_seg);
         if (grid.x > 0) {
             prof_begin(&ck.spans, MDB_KERNEL_MSE_SUPERPOSITION, ws.stream);
-            auto kern = ulp ? (r == 16 ? superposition_kernel<1, 16, 2> : r == 8 ? superposition_kernel<1, 8, 2> : superposition_kernel<1, 2, 2>)
+            auto kern = ulp ? (r == 16 ? superposition_kernel<2, 16, 2> : r == 8 ? superposition_kernel<2, 8, 2> : superposition_kernel<2, 2, 2>)
                             : (r == 8 ? superposition_kernel<1, 8, 1> : superposition_kernel<1, 2, 1>);
             kern<<<grid, SUP_THREADS, LOR_SMEM_BYTES, ws.stream>>>(nullptr, 0, nullptr, 0, ws.resid.as<double>(), d_desc, d_fd,
                                                                   ws.segs.as<Segment>(), ws.lor.as<double>(),
@@ -1112,9 +1285,9 @@ static mdb_status stage_b(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
             prof_end(&ck.spans, ws.stream, -1.0);  // work = sum(points * kept), known in finish_chunk
         }
         prof_begin(&ck.spans, MDB_KERNEL_MSE_REDUCE, ws.stream);
-        if (ulp)  // default mode: CTA-wide tree per range instead of the ordered fold (mse_reduce_fast_kernel)
-            mse_reduce_fast_kernel<<<(unsigned)S, MSE_FAST_THREADS, 0, ws.stream>>>(d_fd, ws.segs.as<Segment>(), ws.resid.as<double>(),
-                                                                                ws.mse.as<double>(), (int)S);
+        if (ulp)  // few-ulp mode: fold the CTA sums K7 left behind (mse_partials_kernel)
+            mse_partials_kernel<<<(unsigned)((S + MSE_PART_WARPS - 1) / MSE_PART_WARPS), 32 * MSE_PART_WARPS, 0, ws.stream>>>(
+                d_fd, ws.segs.as<Segment>(), ws.resid.as<double>(), ws.mse.as<double>(), (int)S, per_block);
         else
             mse_reduce_kernel<<<(unsigned)((S + MSE_WARPS - 1) / MSE_WARPS), 32 * MSE_WARPS, 0, ws.stream>>>(d_fd, ws.segs.as<Segment>(),
                                                                                   ws.resid.as<double>(), ws.mse.as<double>(), (int)S);
@@ -1181,6 +1354,11 @@ static size_t chunk_size_for(const std::vector<HostSpec> &hs)
 static mdb_status build_host_specs(const mdb_deconvoluter &dc, const mdb_spectrum_view *sp, size_t n_spec,
                                    int memory, std::vector<HostSpec> &hs)
 {
+    // the kernels take the smoothing settings as int: larger values are valid in the reference (usize) but
+    // would run for years there too -- refuse them instead of letting the casts wrap
+    if (dc.smoothing.kind == MDB_SMOOTHING_MOVING_AVERAGE
+        && (dc.smoothing.iterations > (uint64_t)INT_MAX || dc.smoothing.window_size > (uint64_t)INT_MAX))
+        return fail(MDB_ERR_UNSUPPORTED, "moving average: iterations and window size above 2^31 - 1 are not supported");
     hs.resize(n_spec);
     std::map<const double *, std::pair<double, double>> x01;
     for (size_t s = 0; s < n_spec; ++s) {
@@ -1213,9 +1391,40 @@ static mdb_status build_host_specs(const mdb_deconvoluter &dc, const mdb_spectru
     return MDB_OK;
 }
 
-// The chunked pipeline over a prepared list of spectra.  Up to eight workspaces (one stream each)
+// Submit the gather of a chunk's pageable rows into its workspace's page-locked staging area.
+static mdb_status prepare_staging(Chunk &ck, const std::vector<HostSpec> &hs, Stager &stager)
+{
+    Workspace &ws = *ck.ws;
+    auto job = std::make_shared<StageJob>();
+    const size_t S = ck.count;
+    job->src.resize(S); job->len.resize(S); job->off.resize(S); job->part_of_row.resize(S);
+    size_t elems = 0, part_elems = 0;
+    const size_t PART_ELEMS = ((size_t)32 << 20) / 8;
+    for (size_t s = 0; s < S; ++s) {
+        const HostSpec &h = hs[ck.first + s];
+        job->src[s] = h.y; job->len[s] = h.n; job->off[s] = elems;  // the layout of ws.y in stage_a
+        elems += align_up(h.n, 16);
+        part_elems += align_up(h.n, 16);
+        job->part_of_row[s] = (int)job->part_end.size();
+        if (part_elems >= PART_ELEMS || s + 1 == S) { job->part_end.push_back(s + 1); part_elems = 0; }
+    }
+    job->part_left.reset(new std::atomic<int>[job->part_end.size()]);
+    for (size_t pt = 0, row0 = 0; pt < job->part_end.size(); ++pt) {
+        job->part_left[pt].store((int)(job->part_end[pt] - row0));
+        row0 = job->part_end[pt];
+    }
+    CUDA_TRY(ws.h_stage.ensure(elems * 8));
+    job->dst = ws.h_stage.as<double>();
+    ck.stage_job = job;
+    stager.submit(job);
+    return MDB_OK;
+}
+
+// The chunked pipeline over a prepared list of spectra.  Up to eight workspaces (two streams each)
 // in flight: stage A of chunk k+1 is queued before the host waits for the counts of chunk k, and
-// older chunks are unpacked while the younger ones run their fit / MSE kernels.
+// older chunks are unpacked while the younger ones run their fit / MSE kernels.  With pageable
+// host rows the chunks are CREATED one further ahead, so that the staging threads gather chunk
+// k+2 while chunk k+1 is in stage A.
 static mdb_status run_pipeline(const mdb_deconvoluter &dc, const std::vector<HostSpec> &hs, int memory,
                                std::vector<SpecResult> &results)
 {
@@ -1224,6 +1433,23 @@ static mdb_status run_pipeline(const mdb_deconvoluter &dc, const std::vector<Hos
     size_t depth = 8;
     if (const char *env = std::getenv("MDB_PIPELINE_DEPTH"))
         if (std::atoi(env) >= 1) depth = (size_t)std::min(std::atoi(env), 32);
+    // Pageable rows?  (probed on the first and the last spectrum; a chunk that mixes kinds is still
+    // handled, row kinds are re-probed per chunk)
+    const bool serial = depth == 1;  // strictly serial (per-kernel profiling): A(k) B(k) finish(k) A(k+1)
+    bool any_pageable = false;
+    if (memory == MDB_MEM_HOST) any_pageable = !host_rows_pinned(hs, 0, 1) || !host_rows_pinned(hs, n_spectra - 1, 1);
+    const size_t look = (any_pageable && !serial) ? 1 : 0;  // chunks created (and gathered) ahead of their stage A
+    const size_t ring = depth + look;                       // workspaces
+    std::unique_ptr<Stager> stager;
+    if (any_pageable) {
+        size_t bytes = 0;
+        for (auto &h : hs) bytes += h.n * 8;
+        const unsigned hw = std::max(2u, std::thread::hardware_concurrency());
+        size_t n_thr = std::max<size_t>(1, std::min<size_t>(8, hw / 2 / (unsigned)std::max(1, t_pipeline_peers)));
+        if (const char *env = std::getenv("MDB_STAGE_THREADS")) if (std::atoi(env) >= 1) n_thr = (size_t)std::min(std::atoi(env), 64);
+        if (bytes < ((size_t)4 << 20)) n_thr = 1;  // small calls: one helper is plenty
+        stager.reset(new Stager(n_thr));
+    }
     // Chunk size: starts at chunk_size_for() and, unless pinned by MDB_CHUNK_SPECTRA, is re-derived
     // from the first chunk's selected-peak counts so that a chunk carries about TARGET Lorentzian
     // evaluations (~12 ms of FP64 work): many-peak spectra get small chunks (fine-grained overlap
@@ -1231,32 +1457,45 @@ static mdb_status run_pipeline(const mdb_deconvoluter &dc, const std::vector<Hos
     // latency amortised).  Measured in profiles/depth_sweep_r1_*.txt.
     const double TARGET_EVALS = 1.8e10;
     const bool pinned_size = std::getenv("MDB_CHUNK_SPECTRA") && std::atoi(std::getenv("MDB_CHUNK_SPECTRA")) > 0;
-    const size_t csz_first = chunk_size_for(hs);
-    size_t csz = csz_first;
+    size_t csz = chunk_size_for(hs);
     std::vector<Workspace *> wss;
+    std::vector<Chunk> chunks;
+    chunks.reserve(n_spectra / 16 + 2);
     auto cleanup = [&]() {
+        stager.reset();  // joins the staging threads before their buffers go back to the pool
         for (Workspace *w : wss)
             if (w) { cudaStreamSynchronize(w->stream); release_workspace(w); }
     };
-    std::vector<Chunk> chunks;
-    chunks.reserve(n_spectra / 16 + 2);
     size_t next_first = 0;
-    auto make_chunk = [&]() -> mdb_status {  // appends the next chunk; its workspace is that of chunk k - depth
-        Chunk ck;
+    // Appends the next chunk.  Its workspace is that of chunk k - ring, which is finished first.
+    auto make_chunk = [&]() -> mdb_status {
         const size_t k = chunks.size();
-        if (k < depth) {
+        if (k >= ring && !chunks[k - ring].finished) {
+            mdb_status s2 = finish_chunk(chunks[k - ring], results, true);
+            if (s2 != MDB_OK) return s2;
+        }
+        if (k < ring) {
             Workspace *w = nullptr;
             mdb_status s2 = acquire_workspace(&w);
             if (s2 != MDB_OK) return s2;
             wss.push_back(w);
         }
-        ck.ws = wss[k % depth];
+        Chunk ck;
+        ck.ws = wss[k % ring];
         ck.first = next_first;
         size_t count = std::min(csz, n_spectra - next_first);
         if (n_spectra - next_first - count < csz / 4) count = n_spectra - next_first;  // no tiny straggler chunk
         ck.count = count;
         next_first += count;
         chunks.push_back(std::move(ck));
+        if (stager && !host_rows_pinned(hs, chunks.back().first, count)) return prepare_staging(chunks.back(), hs, *stager);
+        return MDB_OK;
+    };
+    auto ensure_created = [&](size_t upto) -> mdb_status {  // chunks 0..upto exist (as far as the batch reaches)
+        while (chunks.size() <= upto && next_first < n_spectra) {
+            mdb_status s2 = make_chunk();
+            if (s2 != MDB_OK) return s2;
+        }
         return MDB_OK;
     };
     auto retune = [&](const Chunk &ck) {
@@ -1268,30 +1507,24 @@ static mdb_status run_pipeline(const mdb_deconvoluter &dc, const std::vector<Hos
         const size_t mem_cap = std::max<size_t>(1, ((size_t)1536 << 20) / (48 * max_n + 4096));
         csz = std::max<size_t>(std::min<size_t>(32, mem_cap), std::min({want, (size_t)512, mem_cap}));
     };
-    if ((st = make_chunk()) != MDB_OK) { cleanup(); return st; }
-    st = stage_a(chunks[0], hs, dc, memory, false);
+    st = ensure_created(look);
+    if (st == MDB_OK) st = stage_a(chunks[0], hs, dc, memory, false);
     for (size_t k = 0; st == MDB_OK && k < chunks.size(); ++k) {
-        if (depth == 1) {  // strictly serial (used for per-kernel profiling): A(k) B(k) finish(k) A(k+1)
+        if (serial) {
             st = stage_b(chunks[k], hs, dc, results, true, nullptr);
             if (st == MDB_OK) st = finish_chunk(chunks[k], results, true);
             if (st == MDB_OK && k == 0) retune(chunks[0]);
-            if (st == MDB_OK && next_first < n_spectra) {
-                st = make_chunk();
-                if (st == MDB_OK) st = stage_a(chunks[k + 1], hs, dc, memory, false);
-            }
+            if (st == MDB_OK) st = ensure_created(k + 1);
+            if (st == MDB_OK && k + 1 < chunks.size()) st = stage_a(chunks[k + 1], hs, dc, memory, false);
             continue;
         }
-        if (next_first < n_spectra) {
-            if (k + 1 >= depth) st = finish_chunk(chunks[k + 1 - depth], results, true);  // frees that workspace
-            if (st == MDB_OK) st = make_chunk();
-            if (st == MDB_OK) st = stage_a(chunks[k + 1], hs, dc, memory, false);
-        }
+        st = ensure_created(k + 1 + look);  // finishes the chunks whose workspaces are needed
+        if (st == MDB_OK && k + 1 < chunks.size()) st = stage_a(chunks[k + 1], hs, dc, memory, false);
         if (st == MDB_OK) st = stage_b(chunks[k], hs, dc, results, true, nullptr);
         if (st == MDB_OK && k == 0) retune(chunks[0]);
     }
-    if (depth > 1)
-        for (size_t k = (chunks.size() >= depth ? chunks.size() - depth : 0); st == MDB_OK && k < chunks.size(); ++k)
-            if (chunks[k].stage_b_launched && !chunks[k].finished) st = finish_chunk(chunks[k], results, true);
+    for (size_t k = 0; st == MDB_OK && k < chunks.size(); ++k)
+        if (chunks[k].stage_b_launched && !chunks[k].finished) st = finish_chunk(chunks[k], results, true);
     cleanup();
     return st;
 }
@@ -1363,12 +1596,12 @@ static mdb_status run_small(const mdb_deconvoluter &dc, const std::vector<HostSp
         // ---- layout of the packed input blob (same offsets on the host and on the device)
         size_t int_elems = 0;
         std::vector<size_t> ig_off(S), rg_off(S);
-        std::map<const double *, size_t> x_map;  // caller x pointer -> row index
+        std::map<std::pair<const double *, size_t>, size_t> x_map;  // (caller x pointer, length) -> row index
         for (size_t s = 0; s < S; ++s) {
             const HostSpec &h = hs[first + s];
             ig_off[s] = int_elems; int_elems += h.ig.size();
             rg_off[s] = int_elems; int_elems += 2 * h.ranges.size();
-            if (memory == MDB_MEM_HOST && !x_map.count(h.x)) { const size_t k = x_map.size(); x_map[h.x] = k; }
+            if (memory == MDB_MEM_HOST && !x_map.count({h.x, h.n})) { const size_t k = x_map.size(); x_map[{h.x, h.n}] = k; }
         }
         const size_t off_small = align_up(S * sizeof(SpecDesc), 16);
         const size_t off_int = off_small + align_up(S * sizeof(SmallDesc), 16);
@@ -1395,7 +1628,7 @@ static mdb_status run_small(const mdb_deconvoluter &dc, const std::vector<HostSp
             const HostSpec &h = hs[first + s];
             SpecDesc &d = descs[s];
             if (memory == MDB_MEM_HOST) {
-                d.x = reinterpret_cast<const double *>(db + off_x) + x_map[h.x] * row;
+                d.x = reinterpret_cast<const double *>(db + off_x) + x_map[{h.x, h.n}] * row;
                 d.y = reinterpret_cast<const double *>(db + off_y) + s * row;
                 std::memcpy(hb + off_y + s * row * 8, h.y, h.n * 8);
             } else {
@@ -1429,12 +1662,7 @@ static mdb_status run_small(const mdb_deconvoluter &dc, const std::vector<HostSp
         }
         std::memcpy(h_desc, descs.data(), S * sizeof(SpecDesc));
         if (memory == MDB_MEM_HOST)
-            for (auto &kv : x_map) {
-                size_t n = 0;
-                for (size_t s = 0; s < S; ++s)
-                    if (hs[first + s].x == kv.first) { n = hs[first + s].n; break; }
-                std::memcpy(hb + off_x + kv.second * row * 8, kv.first, n * 8);
-            }
+            for (auto &kv : x_map) std::memcpy(hb + off_x + kv.second * row * 8, kv.first.first, kv.first.second * 8);
         // (letting the kernel pull its rows out of the mapped staging blob instead was measured: 32 KB
         // of zero-copy reads cost 13 us inside the kernel, the DMA plus its launch about 6)
         CUDA_TRY(counted_memcpy_async(db, hb, in_bytes, cudaMemcpyHostToDevice, ws.stream));
@@ -1455,7 +1683,7 @@ static mdb_status run_small(const mdb_deconvoluter &dc, const std::vector<HostSp
         small_fused_kernel<<<(unsigned)S, SMALL_THREADS, smem, ws.stream>>>(
             d_desc, reinterpret_cast<const SmallDesc *>(db + off_small), n_al, dc.selection.kind,
             smooth_fused ? (int)dc.smoothing.iterations : 0, (int)dc.smoothing.window_size,
-            (!dc.exact_mse && mdb_superposition_mode() == MDB_SUPERPOSITION_FAST) ? 1 : 0, d_stamps);
+            dc.sup_mode == MDB_SUPERPOSITION_FAST ? 1 : 0, d_stamps);
         LAUNCH_CHECK();
         prof_end(&spans, ws.stream, (double)S);
         CUDA_TRY(cudaStreamSynchronize(ws.stream));
@@ -1496,37 +1724,6 @@ static mdb_status run_small(const mdb_deconvoluter &dc, const std::vector<HostSp
 // ---------------------------------------------------------------------------------------------
 // In-process multi-GPU sharding (host-memory batches only)
 // ---------------------------------------------------------------------------------------------
-// ---------------------------------------------------------------------------------------------
-// Arithmetic of K7 (the MSE superposition) and K8 (superposition_vec); the fit is always exact.
-// ---------------------------------------------------------------------------------------------
-static int initial_superposition_mode()
-{
-    const char *env = std::getenv("MDB_SUPERPOSITION");
-    if (env && std::strcmp(env, "exact") == 0) return MDB_SUPERPOSITION_EXACT;
-    if (env && std::strcmp(env, "fast") == 0) return MDB_SUPERPOSITION_FAST;
-    return MDB_SUPERPOSITION_FAST;
-}
-static std::atomic<int> g_superposition_mode{-1};
-
-extern "C" int mdb_superposition_mode(void)
-{
-    int m = g_superposition_mode.load();
-    if (m < 0) {
-        m = initial_superposition_mode();
-        int expected = -1;
-        if (!g_superposition_mode.compare_exchange_strong(expected, m)) m = expected;
-    }
-    return m;
-}
-
-extern "C" mdb_status mdb_set_superposition_mode(int mode)
-{
-    if (mode != MDB_SUPERPOSITION_EXACT && mode != MDB_SUPERPOSITION_FAST)
-        return fail(MDB_ERR_INVALID_ARGUMENT, "mdb_set_superposition_mode: unknown mode");
-    g_superposition_mode.store(mode);
-    return MDB_OK;
-}
-
 static std::atomic<int> g_device_policy{1};  // 1 = the calling thread's current device; 0 = all visible; n = first n
 
 extern "C" mdb_status mdb_set_device_count(int n)
@@ -1617,6 +1814,11 @@ extern "C" mdb_status mdb_deconvolute_spectra(const mdb_deconvoluter *d, const m
     std::unique_ptr<mdb_batch> batch(new mdb_batch());
     batch->r.resize(n_spectra);
     if (n_spectra == 0) { *out = batch.release(); return MDB_OK; }
+    // the call works on its own copy of the settings: the arithmetic of an unpinned deconvoluter is the
+    // process default AS OF NOW, and stays that for the whole call whatever other threads set meanwhile
+    mdb_deconvoluter dc_local = *d;
+    if (dc_local.sup_mode < 0 && (st = default_superposition_mode(&dc_local.sup_mode)) != MDB_OK) return st;
+    d = &dc_local;
     std::vector<HostSpec> hs;
     if ((st = build_host_specs(*d, spectra, n_spectra, memory, hs)) != MDB_OK) return st;
 
@@ -1639,6 +1841,7 @@ extern "C" mdb_status mdb_deconvolute_spectra(const mdb_deconvoluter *d, const m
                     msgs[dev] = "cudaSetDevice(" + std::to_string(dev) + ") failed";
                     return;
                 }
+                t_pipeline_peers = n_dev;
                 std::vector<HostSpec> shard(hs.begin() + lo, hs.begin() + hi);
                 std::vector<SpecResult> res(hi - lo);
                 sts[dev] = run(*d, shard, memory, res);
@@ -1690,12 +1893,15 @@ extern "C" mdb_status mdb_deconvoluter_optimize_settings(mdb_deconvoluter *d, co
     CUDA_TRY(ysb.ensure(3 * (size_t)max_iters * stride * 8));
     CUDA_TRY(jobb.ensure(3 * sizeof(SmoothAllJob)));
     const double *dx = spectrum->chemical_shifts, *dy = spectrum->intensities;
-    cudaStream_t stream = nullptr;  // the legacy default stream orders these few preparatory operations
+    Workspace *prep = nullptr;  // its stream orders the preparatory copies and the all-passes smoothing
+    if ((st = acquire_workspace(&prep)) != MDB_OK) return st;
+    struct PrepGuard { Workspace *w; ~PrepGuard() { cudaStreamSynchronize(w->stream); release_workspace(w); } } prep_guard{prep};
+    cudaStream_t stream = prep->stream;
     if (memory == MDB_MEM_HOST) {
         CUDA_TRY(xb.ensure(stride * 8));
         CUDA_TRY(yb.ensure(stride * 8));
-        CUDA_TRY(counted_memcpy(xb.p, spectrum->chemical_shifts, n * 8, cudaMemcpyHostToDevice));
-        CUDA_TRY(counted_memcpy(yb.p, spectrum->intensities, n * 8, cudaMemcpyHostToDevice));
+        CUDA_TRY(counted_memcpy_async(xb.p, spectrum->chemical_shifts, n * 8, cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(counted_memcpy_async(yb.p, spectrum->intensities, n * 8, cudaMemcpyHostToDevice, stream));
         dx = xb.as<double>();
         dy = yb.as<double>();
     }
@@ -1708,10 +1914,10 @@ extern "C" mdb_status mdb_deconvoluter_optimize_settings(mdb_deconvoluter *d, co
         jobs[w].iters = max_iters;
         jobs[w].window = windows[w];
     }
-    CUDA_TRY(counted_memcpy(jobb.p, jobs, sizeof(jobs), cudaMemcpyHostToDevice));
+    CUDA_TRY(counted_memcpy_async(jobb.p, jobs, sizeof(jobs), cudaMemcpyHostToDevice, stream));  // `jobs` outlives the sync below
     smooth_all_passes_kernel<<<3, 32, 0, stream>>>(jobb.as<SmoothAllJob>());
     LAUNCH_CHECK();
-    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaStreamSynchronize(stream));
 
     // ---- the 810 variants in the reference's iteration order: smoothing (iterations outer, window
     // inner), then threshold, then fit iterations
@@ -1723,10 +1929,14 @@ extern "C" mdb_status mdb_deconvoluter_optimize_settings(mdb_deconvoluter *d, co
                 for (int fit = 5; fit <= 15; fit += 5)
                     variants.push_back({iterations, w, 5.0 + (double)c * (8.0 - 5.0) / 9.0, fit});
     mdb_deconvoluter work = *d;
-    work.exact_mse = true;
+    work.sup_mode = MDB_SUPERPOSITION_EXACT;  // the argmin compares MSEs: always the reference's bit patterns
+    work.fit_arith = MDB_FIT_EXACT;
     work.selection.kind = MDB_SELECTION_NOISE_SCORE_FILTER;
     work.selection.scoring_method = MDB_SCORING_MINIMUM_SUM;
-    work.smoothing.kind = MDB_SMOOTHING_MOVING_AVERAGE;
+    // the reference calls set_smoothing_settings(variant) before every run (deconvoluter.rs:787-803): the
+    // caller's own window must not decide the `n < window / 2` panic check; the variants' windows are
+    // 3, 5 and 7, which no admissible spectrum (n >= 5) trips
+    work.smoothing = {MDB_SMOOTHING_MOVING_AVERAGE, 2, 7};
     mdb_spectrum_view view = *spectrum;
     view.chemical_shifts = dx;
     view.intensities = dy;
@@ -1756,50 +1966,173 @@ extern "C" mdb_status mdb_deconvoluter_optimize_settings(mdb_deconvoluter *d, co
 }
 
 // ---------------------------------------------------------------------------------------------
-// superposition_vec
+// superposition_vec  (lorentzian.rs:631-635, 656-663)
 // ---------------------------------------------------------------------------------------------
-extern "C" mdb_status mdb_superposition_vec(const double *x, size_t n, const mdb_lorentzian *lor, size_t p,
-                                            double *out, int memory)
+using SupKernel = void (*)(const double *, long long, const double *, int, double *, const SpecDesc *, const FitDesc *,
+                           const Segment *, const double *, const int *);
+
+// Points per thread from the size of the whole job on this device (every shape gives the same bits).
+static int superposition_points_per_thread(size_t n, bool ulp)
+{
+    const size_t blocks8 = (n + (size_t)SUP_THREADS * 8 - 1) / ((size_t)SUP_THREADS * 8);
+    return (ulp && blocks8 >= (size_t)8 * sm_count() && !std::getenv("MDB_SUP_R8")) ? 16 : blocks8 >= (size_t)2 * sm_count() ? 8 : 2;
+}
+static SupKernel superposition_kernel_for(int r, bool ulp)
+{
+    return ulp ? (r == 16 ? superposition_kernel<0, 16, 2> : r == 8 ? superposition_kernel<0, 8, 2> : superposition_kernel<0, 2, 2>)
+               : (r == 8 ? superposition_kernel<0, 8, 1> : superposition_kernel<0, 2, 1>);
+}
+
+// One slice of a HOST-memory grid on the calling thread's current device: the parameter table goes
+// up once, the slice streams through in chunks over three streams (H2D of chunk c+1 and D2H of chunk
+// c-1 overlap the kernel of chunk c; the kernels of neighbouring chunks overlap each other's tails).
+static mdb_status superposition_host_slice(const double *x, size_t n, const mdb_lorentzian *lor, size_t p, double *out, bool ulp)
+{
+    constexpr int NS = 3;
+    Workspace *ws[NS] = {nullptr, nullptr, nullptr};
+    struct Guard {
+        Workspace **w;
+        ~Guard() { for (int i = 0; i < NS; ++i) if (w[i]) { cudaStreamSynchronize(w[i]->stream); release_workspace(w[i]); } }
+    } guard{ws};
+    mdb_status st;
+    for (int i = 0; i < NS; ++i)
+        if ((st = acquire_workspace(&ws[i])) != MDB_OK) return st;
+    const int r = superposition_points_per_thread(n, ulp);
+    const size_t per_block = (size_t)SUP_THREADS * r;
+    // chunk: about an eighth of the slice, between 64 CTAs' worth and 2^21 points, a multiple of a CTA's points
+    size_t chunk = std::max<size_t>(64 * per_block, std::min<size_t>((size_t)1 << 21, (n + 7) / 8));
+    if (const char *env = std::getenv("MDB_SUP_CHUNK")) if (std::atoll(env) > 0) chunk = (size_t)std::atoll(env);
+    chunk = (chunk + per_block - 1) / per_block * per_block;
+    if ((chunk + per_block - 1) / per_block > 0x7fffffffull) return fail(MDB_ERR_INVALID_ARGUMENT, "grid too large");
+    CUDA_TRY(ws[0]->lor.ensure(std::max<size_t>(p, 1) * 24));
+    if (p) CUDA_TRY(counted_memcpy_async(ws[0]->lor.p, lor, p * 24, cudaMemcpyHostToDevice, ws[0]->stream));
+    CUDA_TRY(cudaEventRecord(ws[0]->ev_a, ws[0]->stream));
+    SupKernel kern = superposition_kernel_for(r, ulp);
+    std::vector<ProfSpan> spans;
+    size_t c = 0;
+    for (size_t lo = 0; lo < n; lo += chunk, ++c) {
+        Workspace &w = *ws[c % NS];
+        const size_t cnt = std::min(chunk, n - lo);
+        if (c < NS) {
+            CUDA_TRY(w.x.ensure(std::min(chunk, n) * 8));
+            CUDA_TRY(w.ys.ensure(std::min(chunk, n) * 8));
+            if (c > 0) CUDA_TRY(cudaStreamWaitEvent(w.stream, ws[0]->ev_a, 0));  // the parameter table has landed
+        }
+        CUDA_TRY(counted_memcpy_async(w.x.p, x + lo, cnt * 8, cudaMemcpyHostToDevice, w.stream));
+        prof_begin(&spans, MDB_KERNEL_SUPERPOSITION_VEC, w.stream);
+        kern<<<(unsigned)((cnt + per_block - 1) / per_block), SUP_THREADS, LOR_SMEM_BYTES, w.stream>>>(
+            w.x.as<double>(), (long long)cnt, ws[0]->lor.as<double>(), (int)p, w.ys.as<double>(), nullptr, nullptr, nullptr, nullptr, nullptr);
+        LAUNCH_CHECK();
+        prof_end(&spans, w.stream, (double)cnt * (double)p);
+        CUDA_TRY(counted_memcpy_async(out + lo, w.ys.p, cnt * 8, cudaMemcpyDeviceToHost, w.stream));
+    }
+    for (int i = 0; i < NS; ++i) CUDA_TRY(cudaStreamSynchronize(ws[i]->stream));
+    prof_resolve(&spans);
+    return MDB_OK;
+}
+
+extern "C" mdb_status mdb_superposition_vec_mode(const double *x, size_t n, const mdb_lorentzian *lor, size_t p,
+                                                 double *out, int memory, int mode)
 {
     if ((n && (!x || !out)) || (p && !lor)) return fail(MDB_ERR_INVALID_ARGUMENT, "mdb_superposition_vec: null argument");
     if (p >= ((size_t)1 << 31)) return fail(MDB_ERR_INVALID_ARGUMENT, "too many lorentzians");
+    if (memory != MDB_MEM_HOST && memory != MDB_MEM_DEVICE) return fail(MDB_ERR_INVALID_ARGUMENT, "unknown memory kind");
+    if (mode != MDB_SUPERPOSITION_EXACT && mode != MDB_SUPERPOSITION_FAST)
+        return fail(MDB_ERR_INVALID_ARGUMENT, "mdb_superposition_vec_mode: unknown mode");
     mdb_status st = require_device();
     if (st != MDB_OK) return st;
     if (n == 0) return MDB_OK;
+    const bool ulp = mode == MDB_SUPERPOSITION_FAST;
+    if (memory == MDB_MEM_HOST) {
+        // par_superposition_vec's rayon-over-points (lorentzian.rs:660-662) as grid slices over the GPUs
+        // mdb_set_device_count allows: at least 2^16 points per device, parameters replicated, no exchange
+        const int n_dev = devices_to_use(n >> 15);
+        if (n_dev <= 1) return superposition_host_slice(x, n, lor, p, out, ulp);
+        std::vector<mdb_status> sts(n_dev, MDB_OK);
+        std::vector<std::string> msgs(n_dev);
+        std::vector<std::thread> threads;
+        for (int dev = 0; dev < n_dev; ++dev)
+            threads.emplace_back([&, dev]() {
+                const size_t lo = (size_t)dev * n / n_dev, hi = (size_t)(dev + 1) * n / n_dev;
+                if (cudaSetDevice(dev) != cudaSuccess) {
+                    sts[dev] = MDB_ERR_CUDA;
+                    msgs[dev] = "cudaSetDevice(" + std::to_string(dev) + ") failed";
+                    return;
+                }
+                sts[dev] = superposition_host_slice(x + lo, hi - lo, lor, p, out + lo, ulp);
+                if (sts[dev] != MDB_OK) msgs[dev] = g_last_error;  // thread-local in the worker
+            });
+        for (auto &t : threads) t.join();
+        for (int dev = 0; dev < n_dev; ++dev)
+            if (sts[dev] != MDB_OK) return fail(sts[dev], "device " + std::to_string(dev) + ": " + msgs[dev]);
+        return MDB_OK;
+    }
     Workspace *ws = nullptr;
     if ((st = acquire_workspace(&ws)) != MDB_OK) return st;
     struct Guard { Workspace *w; ~Guard() { cudaStreamSynchronize(w->stream); release_workspace(w); } } guard{ws};
-    const double *dx = x, *dl = (const double *)lor;
-    double *dout = out;
-    if (memory == MDB_MEM_HOST) {
-        CUDA_TRY(ws->x.ensure(n * 8));
-        CUDA_TRY(ws->ys.ensure(n * 8));
-        CUDA_TRY(counted_memcpy_async(ws->x.p, x, n * 8, cudaMemcpyHostToDevice, ws->stream));
-        dx = ws->x.as<double>();
-        dout = ws->ys.as<double>();
-    }
-    if (memory == MDB_MEM_HOST || ((uintptr_t)lor & 15) != 0) {  // the kernel's bulk copies need 16-byte alignment
+    const double *dl = (const double *)lor;
+    if (((uintptr_t)lor & 15) != 0) {  // the kernel's bulk copies need 16-byte alignment
         CUDA_TRY(ws->lor.ensure(std::max<size_t>(p, 1) * 24));
-        if (p) CUDA_TRY(counted_memcpy_async(ws->lor.p, lor, p * 24, memory == MDB_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, ws->stream));
+        if (p) CUDA_TRY(counted_memcpy_async(ws->lor.p, lor, p * 24, cudaMemcpyDeviceToDevice, ws->stream));
         dl = ws->lor.as<double>();
     }
-    const size_t blocks8 = (n + (size_t)SUP_THREADS * 8 - 1) / ((size_t)SUP_THREADS * 8);
-    const bool ulp = mdb_superposition_mode() == MDB_SUPERPOSITION_FAST;
-    const int r = (ulp && blocks8 >= (size_t)8 * sm_count() && !std::getenv("MDB_SUP_R8")) ? 16 : blocks8 >= (size_t)2 * sm_count() ? 8 : 2;
+    const int r = superposition_points_per_thread(n, ulp);
     const size_t per_block = (size_t)SUP_THREADS * r;
     const size_t blocks = (n + per_block - 1) / per_block;
     if (blocks > 0x7fffffffull) return fail(MDB_ERR_INVALID_ARGUMENT, "grid too large");
     std::vector<ProfSpan> spans;
     prof_begin(&spans, MDB_KERNEL_SUPERPOSITION_VEC, ws->stream);
-    auto kern = ulp ? (r == 16 ? superposition_kernel<0, 16, 2> : r == 8 ? superposition_kernel<0, 8, 2> : superposition_kernel<0, 2, 2>)
-                    : (r == 8 ? superposition_kernel<0, 8, 1> : superposition_kernel<0, 2, 1>);
-    kern<<<(unsigned)blocks, SUP_THREADS, LOR_SMEM_BYTES, ws->stream>>>(dx, (long long)n, dl, (int)p, dout, nullptr, nullptr,
-                                                                      nullptr, nullptr, nullptr);
+    superposition_kernel_for(r, ulp)<<<(unsigned)blocks, SUP_THREADS, LOR_SMEM_BYTES, ws->stream>>>(
+        x, (long long)n, dl, (int)p, out, nullptr, nullptr, nullptr, nullptr, nullptr);
     LAUNCH_CHECK();
     prof_end(&spans, ws->stream, (double)n * (double)p);
-    if (memory == MDB_MEM_HOST) CUDA_TRY(counted_memcpy_async(out, dout, n * 8, cudaMemcpyDeviceToHost, ws->stream));
     CUDA_TRY(cudaStreamSynchronize(ws->stream));
     prof_resolve(&spans);
+    return MDB_OK;
+}
+
+extern "C" mdb_status mdb_superposition_vec(const double *x, size_t n, const mdb_lorentzian *lor, size_t p,
+                                            double *out, int memory)
+{
+    int mode = 0;
+    mdb_status st = default_superposition_mode(&mode);
+    if (st != MDB_OK) return st;
+    return mdb_superposition_vec_mode(x, n, lor, p, out, memory, mode);
+}
+
+// FP64 instruction rate of the current device (bench.py's measured denominator): every SM fully
+// occupied by 16 independent chains per thread of nothing but DFMA, then DADD; CUDA events on the
+// launching stream; best of three.
+extern "C" mdb_status mdb_measure_fp64_rate(double *dfma_per_s, double *dadd_per_s)
+{
+    mdb_status st = require_device();
+    if (st != MDB_OK) return st;
+    Workspace *ws = nullptr;
+    if ((st = acquire_workspace(&ws)) != MDB_OK) return st;
+    struct Guard { Workspace *w; ~Guard() { cudaStreamSynchronize(w->stream); release_workspace(w); } } guard{ws};
+    const int blocks = sm_count() * 8, iters = 1 << 14;
+    CUDA_TRY(ws->tmp.ensure((size_t)blocks * RATE_THREADS * 8));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    double best[2] = {0.0, 0.0};
+    for (int kind = 0; kind < 2; ++kind)
+        for (int rep = 0; rep < 4; ++rep) {  // rep 0 warms up
+            CUDA_TRY(cudaEventRecord(e0, ws->stream));
+            if (kind == 0) fp64_rate_kernel<0><<<blocks, RATE_THREADS, 0, ws->stream>>>(ws->tmp.as<double>(), iters, 1.0 + rep);
+            else fp64_rate_kernel<1><<<blocks, RATE_THREADS, 0, ws->stream>>>(ws->tmp.as<double>(), iters, 1.0 + rep);
+            LAUNCH_CHECK();
+            CUDA_TRY(cudaEventRecord(e1, ws->stream));
+            CUDA_TRY(cudaStreamSynchronize(ws->stream));
+            float ms = 0.f;
+            CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+            const double rate = (double)blocks * RATE_THREADS * RATE_CHAINS * (double)iters / ((double)ms * 1e-3);
+            if (rep > 0) best[kind] = std::max(best[kind], rate);
+        }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (dfma_per_s) *dfma_per_s = best[0];
+    if (dadd_per_s) *dadd_per_s = best[1];
     return MDB_OK;
 }
 
@@ -1814,6 +2147,8 @@ extern "C" mdb_status mdb_stage_smooth(const double *values, size_t n, uint64_t 
     mdb_status st = validate_smoothing(sm);
     if (st != MDB_OK) return st;
     if (n < window / 2) return fail(MDB_ERR_REFERENCE_PANIC, "fewer points than half the window");
+    if (iterations > (uint64_t)INT_MAX || window > (uint64_t)INT_MAX)
+        return fail(MDB_ERR_UNSUPPORTED, "moving average: iterations and window size above 2^31 - 1 are not supported");
     if ((st = require_device()) != MDB_OK) return st;
     Workspace *ws = nullptr;
     if ((st = acquire_workspace(&ws)) != MDB_OK) return st;
@@ -1852,6 +2187,8 @@ extern "C" mdb_status mdb_stage_smooth_batch(const double *values_dev, size_t n,
     mdb_smoothing_settings sm = {MDB_SMOOTHING_MOVING_AVERAGE, iterations, window};
     mdb_status st = validate_smoothing(sm);
     if (st != MDB_OK) return st;
+    if (iterations > (uint64_t)INT_MAX || window > (uint64_t)INT_MAX)
+        return fail(MDB_ERR_UNSUPPORTED, "moving average: iterations and window size above 2^31 - 1 are not supported");
     if ((st = require_device()) != MDB_OK) return st;
     Workspace *ws = nullptr;
     if ((st = acquire_workspace(&ws)) != MDB_OK) return st;
@@ -1928,7 +2265,7 @@ extern "C" mdb_status mdb_stage_detect(const double *smoothed, size_t n, int32_t
     // download the per-tile candidate lists and concatenate them in tile order (test-only path)
     const SpecDesc &d = ck.desc[0];
     std::vector<int> tile_cnt(d.n_tiles);
-    CUDA_TRY(cudaStreamSynchronize(ws->stream));
+    CUDA_TRY(cudaStreamSynchronize(ws->stream_a));
     CUDA_TRY(counted_memcpy(tile_cnt.data(), d.tile_cnt, (size_t)d.n_tiles * 4, cudaMemcpyDeviceToHost));
     std::vector<int> pk(3 * (size_t)DETECT_CAP);
     std::vector<double> sc(DETECT_CAP);

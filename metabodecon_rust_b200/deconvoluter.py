@@ -66,6 +66,19 @@ class Deconvoluter:
     def clear_ignore_regions(self) -> None:
         _lib.load().mdb_deconvoluter_clear_ignore_regions(self._h)
 
+    # ---- no counterpart in the reference: arithmetic of the MSE superposition of THIS deconvoluter
+    def set_superposition_mode(self, mode: str) -> None:
+        """Pin the arithmetic of `Deconvolution.mse` for this deconvoluter: "exact" (the reference's bit
+        patterns) or "fast" (few-ulp terms, MSE within ~1e-13 relative).  A deconvoluter that was never
+        pinned follows the process default (`metabodecon_rust_b200.set_superposition_mode`)."""
+        modes = {"exact": _lib.MDB_SUPERPOSITION_EXACT, "fast": _lib.MDB_SUPERPOSITION_FAST}
+        if mode not in modes:
+            raise ValueError("mode must be 'exact' or 'fast'")
+        raise_for_status(_lib.load().mdb_deconvoluter_set_superposition_mode(self._h, modes[mode]), _lib.last_error())
+
+    def superposition_mode(self) -> str:
+        return "fast" if _lib.load().mdb_deconvoluter_superposition_mode(self._h) == _lib.MDB_SUPERPOSITION_FAST else "exact"
+
     def set_threads(self, threads: int) -> None:
         # bindings/deconvoluter.rs:92-106 validates the count; the GPU path has no pool to size.
         if threads <= 1:

@@ -28,16 +28,22 @@ def _as_params(lorentzians) -> np.ndarray:
     return out
 
 
-def superposition_vec_array(x, params: np.ndarray) -> np.ndarray:
-    """GPU superposition of the (P,3) parameter array at x (lorentzian.rs:631-635)."""
+def superposition_vec_array(x, params: np.ndarray, mode=None) -> np.ndarray:
+    """GPU superposition of the (P,3) parameter array at x (lorentzian.rs:631-635).  mode: None = the
+    process default (`set_superposition_mode`), "exact" / "fast" = stated by the caller."""
     lib = _lib.load()
     x = np.ascontiguousarray(x, dtype=np.float64)
     if x.ndim != 1:
         raise ValueError("x must be one-dimensional")
     params = np.ascontiguousarray(params, dtype=np.float64)
     out = np.empty_like(x)
-    st = lib.mdb_superposition_vec(x.ctypes.data, x.size, params.ctypes.data, params.shape[0],
-                                   out.ctypes.data, _lib.MDB_MEM_HOST)
+    if mode is None:
+        st = lib.mdb_superposition_vec(x.ctypes.data, x.size, params.ctypes.data, params.shape[0],
+                                       out.ctypes.data, _lib.MDB_MEM_HOST)
+    else:
+        code = {"exact": _lib.MDB_SUPERPOSITION_EXACT, "fast": _lib.MDB_SUPERPOSITION_FAST}[mode]
+        st = lib.mdb_superposition_vec_mode(x.ctypes.data, x.size, params.ctypes.data, params.shape[0],
+                                            out.ctypes.data, _lib.MDB_MEM_HOST, code)
     raise_for_status(st, _lib.last_error())
     return out
 
@@ -88,14 +94,16 @@ class Lorentzian:
         return self.sfhw / (self.hw2 + d * d)
 
     def evaluate_vec(self, x) -> np.ndarray:  # lorentzian.rs:563-565 (0.0 + t == t)
-        return superposition_vec_array(x, _as_params([self]))
+        # always the exact arithmetic: agrees bit for bit with the scalar `evaluate` above
+        return superposition_vec_array(x, _as_params([self]), mode="exact")
 
     def integral(self) -> float:  # lorentzian.rs:580-582
         return math.pi * self.sf
 
     @staticmethod
     def superposition(x: float, lorentzians) -> float:  # lorentzian.rs:606-611
-        return float(superposition_vec_array(np.array([x], dtype=np.float64), _as_params(lorentzians))[0])
+        # a single point: always the exact arithmetic (the reference's bit pattern)
+        return float(superposition_vec_array(np.array([x], dtype=np.float64), _as_params(lorentzians), mode="exact")[0])
 
     @staticmethod
     def superposition_vec(x, lorentzians) -> np.ndarray:  # lorentzian.rs:631-635

@@ -184,6 +184,20 @@ impl Clone for Deconvoluter {
     }
 }
 
+impl Deconvoluter {
+    /// Pins the arithmetic of `Deconvolution::mse` for THIS deconvoluter (`mdb_deconvoluter_set_superposition_mode`):
+    /// two deconvoluters of one process may differ and run concurrently.  Unpinned ones follow
+    /// `set_exact_superposition`'s process default.
+    pub fn set_exact_mse(&mut self, exact: bool) -> Result<()> {
+        check(unsafe {
+            sys::mdb_deconvoluter_set_superposition_mode(
+                self.handle,
+                if exact { sys::MDB_SUPERPOSITION_EXACT } else { sys::MDB_SUPERPOSITION_FAST },
+            )
+        })
+    }
+}
+
 impl Drop for Deconvoluter {
     fn drop(&mut self) {
         unsafe { sys::mdb_deconvoluter_free(self.handle) }
@@ -199,7 +213,17 @@ pub fn superposition_vec(x: &[f64], lorentzians: &[Lorentzian]) -> Result<Vec<f6
     Ok(out)
 }
 
-/// Arithmetic of `Deconvolution::mse` and `superposition_vec` (include/mdb200.h,
+/// `superposition_vec` with the arithmetic stated by the caller instead of the process default.
+pub fn superposition_vec_with(x: &[f64], lorentzians: &[Lorentzian], exact: bool) -> Result<Vec<f64>> {
+    let mut out = vec![0.0; x.len()];
+    let mode = if exact { sys::MDB_SUPERPOSITION_EXACT } else { sys::MDB_SUPERPOSITION_FAST };
+    check(unsafe {
+        sys::mdb_superposition_vec_mode(x.as_ptr(), x.len(), lorentzians.as_ptr(), lorentzians.len(), out.as_mut_ptr(), sys::MDB_MEM_HOST, mode)
+    })?;
+    Ok(out)
+}
+
+/// Process DEFAULT of the arithmetic of `Deconvolution::mse` and `superposition_vec` (include/mdb200.h,
 /// `mdb_set_superposition_mode`): `true` replays the reference's operators bit for bit, `false`
 /// (the library default) uses half the FP64 instructions and agrees to about 1e-15 relative (1e-13 for the MSE).
 /// Peak sets and Lorentzian parameters are bit-identical in both.

@@ -1,4 +1,4 @@
-//! Raw bindings to `include/mdb200.h` (ABI version 1).  One declaration per exported symbol;
+//! Raw bindings to `include/mdb200.h` (ABI version 2).  One declaration per exported symbol;
 //! see the header for the reference interface (file:line) each one replaces.
 #![allow(non_camel_case_types)]
 
@@ -33,6 +33,9 @@ pub const MDB_MEM_HOST: c_int = 0;
 pub const MDB_MEM_DEVICE: c_int = 1;
 pub const MDB_SUPERPOSITION_EXACT: c_int = 0;
 pub const MDB_SUPERPOSITION_FAST: c_int = 1;
+pub const MDB_FIT_EXACT: c_int = 0;
+pub const MDB_FIT_CORRECTED: c_int = 1;
+pub const MDB_FIT_ULP: c_int = 2;
 
 /// `Lorentzian {sfhw, hw2, maxp}` (metabodecon/src/deconvolution/lorentzian.rs:138-145).
 #[repr(C)]
@@ -92,6 +95,7 @@ extern "C" {
     pub fn mdb_set_device_count(n: c_int) -> mdb_status;
     pub fn mdb_set_superposition_mode(mode: c_int) -> mdb_status;
     pub fn mdb_superposition_mode() -> c_int;
+    pub fn mdb_measure_fp64_rate(dfma_per_s: *mut f64, dadd_per_s: *mut f64) -> mdb_status;
     pub fn mdb_host_alloc(ptr: *mut *mut c_void, bytes: usize) -> mdb_status;
     pub fn mdb_host_free(ptr: *mut c_void) -> mdb_status;
     pub fn mdb_release_workspaces() -> mdb_status;
@@ -129,6 +133,10 @@ extern "C" {
     pub fn mdb_deconvoluter_set_fitting_settings(d: *mut mdb_deconvoluter, s: *const mdb_fitting_settings) -> mdb_status;
     pub fn mdb_deconvoluter_add_ignore_region(d: *mut mdb_deconvoluter, lo: f64, hi: f64) -> mdb_status;
     pub fn mdb_deconvoluter_clear_ignore_regions(d: *mut mdb_deconvoluter);
+    pub fn mdb_deconvoluter_set_superposition_mode(d: *mut mdb_deconvoluter, mode: c_int) -> mdb_status;
+    pub fn mdb_deconvoluter_superposition_mode(d: *const mdb_deconvoluter) -> c_int;
+    pub fn mdb_deconvoluter_set_fit_arithmetic(d: *mut mdb_deconvoluter, kind: c_int) -> mdb_status;
+    pub fn mdb_deconvoluter_fit_arithmetic(d: *const mdb_deconvoluter) -> c_int;
 
     pub fn mdb_batch_len(b: *const mdb_batch) -> usize;
     pub fn mdb_batch_status(b: *const mdb_batch, i: usize) -> mdb_status;
@@ -169,6 +177,15 @@ extern "C" {
         n_lorentzians: usize,
         out: *mut f64,
         memory: c_int,
+    ) -> mdb_status;
+    pub fn mdb_superposition_vec_mode(
+        x: *const f64,
+        n: usize,
+        lorentzians: *const mdb_lorentzian,
+        n_lorentzians: usize,
+        out: *mut f64,
+        memory: c_int,
+        mode: c_int,
     ) -> mdb_status;
 
     pub fn mdb_stage_smooth(values: *const f64, n: usize, iterations: u64, window_size: u64, out: *mut f64) -> mdb_status;

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in include/mdb200.h but not exported"
         assert name in bound, f"{name} declared in include/mdb200.h but not bound in _lib.SIGNATURES"
     assert bound <= set(declared)
-    assert lib.mdb_abi_version() == 1
+    assert lib.mdb_abi_version() == _lib.ABI_VERSION == 2
 
 
 def test_rust_sys_crate_declares_every_header_symbol():
