@@ -360,6 +360,12 @@ def max_threads() -> int:
     return lib().orc_max_threads()
 
 
+def use_cores(n: int) -> int:
+    """Size the OpenMP pool to `n` threads (bench.py: one oracle per rank, cores shared out)."""
+    lib().orc_set_num_threads(C.c_int(max(1, int(n))))
+    return max_threads()
+
+
 def use_all_cores() -> int:
     """Size the OpenMP pool to every core this process may run on (torchrun exports
     OMP_NUM_THREADS=1, which would otherwise make the CPU baseline single-threaded)."""
