@@ -344,7 +344,9 @@ def main():
             out = []
             for i in export:
                 k = lib.mdb_batch_n_lorentzians(batch, i)
-                got = np.ctypeslib.as_array(C.cast(lib.mdb_batch_lorentzians(batch, i), C.POINTER(C.c_double)), (max(k, 1), 3))[:k].copy()
+                got = np.zeros((0, 3))
+                if k:
+                    got = np.ctypeslib.as_array(C.cast(lib.mdb_batch_lorentzians(batch, i), C.POINTER(C.c_double)), (k, 3)).copy()
                 out.append((got, int(lib.mdb_batch_n_peaks(batch, i)), float(lib.mdb_batch_mse(batch, i))))
         lib.mdb_batch_free(batch)
         return tl.value, tp.value, out

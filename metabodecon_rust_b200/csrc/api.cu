@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <climits>
 #include <cmath>
 #include <cstdio>
@@ -64,6 +65,7 @@ static mdb_status fail(mdb_status st, const std::string &msg)
     do {                                                                                          \
         cudaError_t e__ = (expr);                                                                 \
         if (e__ != cudaSuccess) {                                                                 \
+            cudaGetLastError(); /* reported here: do not leave it for the next launch check */    \
             return fail(MDB_ERR_CUDA, std::string(#expr) + " failed: " + cudaGetErrorString(e__)  \
                                           + " (" __FILE__ ":" + std::to_string(__LINE__) + ")");  \
         }                                                                                         \
@@ -806,6 +808,9 @@ struct Chunk {
     bool stage_b_launched = false, finished = false;
     double est_evals = 0.0;            // Lorentzian evaluations of this chunk's fit + MSE kernels (from the counts)
     std::shared_ptr<StageJob> stage_job;  // pageable host rows being gathered into ws->h_stage (null: none)
+    // host clock (ms since the pipeline started) at which stage A was queued, the counts had arrived,
+    // stage B was queued and the results had arrived; written out by MDB_TIMELINE=<file> (tools/timeline.py)
+    double t_a = 0.0, t_counts = 0.0, t_b = 0.0, t_done = 0.0;
     std::vector<ProfSpan> spans;       // per-kernel timing, resolved in finish_chunk
 };
 
@@ -885,6 +890,12 @@ static bool host_rows_pinned(const std::vector<HostSpec> &hs, size_t first, size
         if (attr.type == cudaMemoryTypeUnregistered) return false;
     }
     return true;
+}
+
+static thread_local std::chrono::steady_clock::time_point t_pipeline_origin;
+static double pipeline_ms()
+{
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_pipeline_origin).count();
 }
 
 // Stage A: inputs -> device, smoothing, detection, selection, counts back to the host.
@@ -1011,7 +1022,18 @@ static mdb_status stage_a(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
                     if (hp.n % 16 == 0 && hn.y == hp.y + hp.n) { bytes += hn.n * 8; ++e; }
                     else break;
                 }
-                CUDA_TRY(counted_memcpy_async(y_dst + y_off[s], h0.y, bytes, cudaMemcpyHostToDevice, ws.stream_a));
+                cudaError_t ce = counted_memcpy_async(y_dst + y_off[s], h0.y, bytes, cudaMemcpyHostToDevice, ws.stream_a);
+                if (ce == cudaErrorInvalidValue && e > s + 1) {
+                    // adjacent in the address space but not one page-locked allocation (separately allocated
+                    // rows that happen to touch): a copy may not span two allocations -- row by row instead
+                    cudaGetLastError();
+                    g_h2d_bytes -= bytes;
+                    for (size_t q = s; q < e; ++q)
+                        CUDA_TRY(counted_memcpy_async(y_dst + y_off[q], hs[ck.first + q].y, hs[ck.first + q].n * 8,
+                                                      cudaMemcpyHostToDevice, ws.stream_a));
+                } else {
+                    CUDA_TRY(ce);
+                }
                 s = e;
             }
         }
@@ -1060,6 +1082,7 @@ static mdb_status stage_a(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
     }
     CUDA_TRY(counted_memcpy_async(ws.h_sel_out.p, ws.sel_out.p, S * sizeof(SelectOut), cudaMemcpyDeviceToHost, ws.stream_a));
     CUDA_TRY(cudaEventRecord(ws.ev_a, ws.stream_a));
+    ck.t_a = pipeline_ms();
     return MDB_OK;
 }
 
@@ -1081,6 +1104,7 @@ static mdb_status stage_b(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
     Workspace &ws = *ck.ws;
     const size_t S = ck.count;
     CUDA_TRY(cudaEventSynchronize(ws.ev_a));
+    ck.t_counts = pipeline_ms();
     const SelectOut *so = ws.h_sel_out.as<SelectOut>();
     ck.fdesc.assign(S, FitDesc{});
     ck.segs.clear();
@@ -1302,6 +1326,7 @@ static mdb_status stage_b(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
     }
     CUDA_TRY(cudaEventRecord(ws.ev_b, ws.stream));
     ck.stage_b_launched = true;
+    ck.t_b = pipeline_ms();
     return MDB_OK;
 }
 
@@ -1310,6 +1335,7 @@ static mdb_status finish_chunk(Chunk &ck, std::vector<SpecResult> &results, bool
 {
     Workspace &ws = *ck.ws;
     CUDA_TRY(cudaEventSynchronize(ws.ev_b));
+    ck.t_done = pipeline_ms();
     const int *kept = ws.h_n_kept.as<int>();
     const double *mse = ws.h_mse.as<double>();
     const mdb_lorentzian *lor = ws.h_lor.as<mdb_lorentzian>();
@@ -1430,6 +1456,7 @@ static mdb_status run_pipeline(const mdb_deconvoluter &dc, const std::vector<Hos
 {
     const size_t n_spectra = hs.size();
     mdb_status st = MDB_OK;
+    t_pipeline_origin = std::chrono::steady_clock::now();
     size_t depth = 8;
     if (const char *env = std::getenv("MDB_PIPELINE_DEPTH"))
         if (std::atoi(env) >= 1) depth = (size_t)std::min(std::atoi(env), 32);
@@ -1455,7 +1482,8 @@ static mdb_status run_pipeline(const mdb_deconvoluter &dc, const std::vector<Hos
     // evaluations (~12 ms of FP64 work): many-peak spectra get small chunks (fine-grained overlap
     // of kernel tails across streams), few-peak spectra get large ones (launch and smoothing
     // latency amortised).  Measured in profiles/depth_sweep_r1_*.txt.
-    const double TARGET_EVALS = 1.8e10;
+    double TARGET_EVALS = 1.8e10;
+    if (const char *env = std::getenv("MDB_TARGET_EVALS")) if (std::atof(env) > 0.0) TARGET_EVALS = std::atof(env);  // sweeps
     const bool pinned_size = std::getenv("MDB_CHUNK_SPECTRA") && std::atoi(std::getenv("MDB_CHUNK_SPECTRA")) > 0;
     size_t csz = chunk_size_for(hs);
     std::vector<Workspace *> wss;
@@ -1525,6 +1553,20 @@ static mdb_status run_pipeline(const mdb_deconvoluter &dc, const std::vector<Hos
     }
     for (size_t k = 0; st == MDB_OK && k < chunks.size(); ++k)
         if (chunks[k].stage_b_launched && !chunks[k].finished) st = finish_chunk(chunks[k], results, true);
+    if (const char *path = std::getenv("MDB_TIMELINE")) {  // measurement aid: one line per chunk, appended
+        static std::mutex tl_mutex;
+        std::lock_guard<std::mutex> lock(tl_mutex);
+        if (FILE *f = std::fopen(path, "a")) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            std::fprintf(f, "{\"device\": %d, \"spectra\": %zu, \"total_ms\": %.3f, \"chunks\": [", dev, n_spectra, pipeline_ms());
+            for (size_t k = 0; k < chunks.size(); ++k)
+                std::fprintf(f, "%s[%zu, %zu, %.3f, %.3f, %.3f, %.3f]", k ? ", " : "", chunks[k].first, chunks[k].count,
+                             chunks[k].t_a, chunks[k].t_counts, chunks[k].t_b, chunks[k].t_done);
+            std::fprintf(f, "]}\n");
+            std::fclose(f);
+        }
+    }
     cleanup();
     return st;
 }

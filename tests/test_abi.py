@@ -205,6 +205,43 @@ def test_superposition_mode_switch_is_host_logic():
         assert out == [first, "exact", "True", "exact"], out
 
 
+def test_superposition_mode_is_a_property_of_the_deconvoluter():
+    """Host logic of VERDICT r1 item 7: the mode lives in the handle (pinned) or follows the process
+    default (never pinned); clones inherit; a malformed MDB_SUPERPOSITION is reported, not ignored."""
+    import subprocess
+    import sys
+    lib = _lib.load()
+    a, b = Deconvoluter(), Deconvoluter()
+    before = lib.mdb_superposition_mode()
+    try:
+        assert lib.mdb_set_superposition_mode(_lib.MDB_SUPERPOSITION_FAST) == 0
+        assert a.superposition_mode() == "fast" and b.superposition_mode() == "fast"
+        a.set_superposition_mode("exact")
+        assert a.superposition_mode() == "exact" and b.superposition_mode() == "fast"
+        assert lib.mdb_set_superposition_mode(_lib.MDB_SUPERPOSITION_EXACT) == 0
+        assert b.superposition_mode() == "exact"  # never pinned: follows the default
+        b.set_superposition_mode("fast")
+        assert lib.mdb_set_superposition_mode(_lib.MDB_SUPERPOSITION_FAST) == 0
+        assert a.superposition_mode() == "exact" and b.superposition_mode() == "fast"
+        clone = C.c_void_p()
+        assert lib.mdb_deconvoluter_clone(a._h, C.byref(clone)) == 0
+        assert lib.mdb_deconvoluter_superposition_mode(clone) == _lib.MDB_SUPERPOSITION_EXACT
+        lib.mdb_deconvoluter_free(clone)
+        with pytest.raises(ValueError):
+            a.set_superposition_mode("sloppy")
+        assert lib.mdb_deconvoluter_set_superposition_mode(a._h, 9) != 0
+        assert lib.mdb_deconvoluter_fit_arithmetic(a._h) == _lib.MDB_FIT_EXACT  # the product default
+        assert lib.mdb_deconvoluter_set_fit_arithmetic(a._h, 9) != 0
+    finally:
+        lib.mdb_set_superposition_mode(before if before >= 0 else _lib.MDB_SUPERPOSITION_FAST)
+    code = ("import sys; sys.path.insert(0, %r); from metabodecon_rust_b200 import _lib; lib = _lib.load(); "
+            "print(lib.mdb_superposition_mode()); print(lib.mdb_superposition_vec(None, 0, None, 0, None, 0)); "
+            "print(_lib.last_error())") % ROOT
+    env = dict(os.environ, MDB_SUPERPOSITION="sloppy")
+    out = subprocess.run([sys.executable, "-c", code], env=env, check=True, capture_output=True, text=True).stdout.splitlines()
+    assert int(out[0]) < 0 and int(out[1]) == _lib.MDB_ERR_INVALID_ARGUMENT and "sloppy" in out[2], out
+
+
 def test_product_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "metabodecon_rust_b200")
     for base, _, files in os.walk(pkg):
