@@ -1465,8 +1465,12 @@ static mdb_status run_pipeline(const mdb_deconvoluter &dc, const std::vector<Hos
     const bool serial = depth == 1;  // strictly serial (per-kernel profiling): A(k) B(k) finish(k) A(k+1)
     bool any_pageable = false;
     if (memory == MDB_MEM_HOST) any_pageable = !host_rows_pinned(hs, 0, 1) || !host_rows_pinned(hs, n_spectra - 1, 1);
+    // Stage A runs `ahead` chunks in front of stage B: the first chunks are small (their peak counts
+    // size the later ones), and queueing several of them at once lets their H2D copies and smoothing
+    // latencies overlap instead of costing one round trip each while the GPU has nothing else to do.
+    const size_t ahead = serial ? 0 : std::min<size_t>(3, depth - 1);
     const size_t look = (any_pageable && !serial) ? 1 : 0;  // chunks created (and gathered) ahead of their stage A
-    const size_t ring = depth + look;                       // workspaces
+    const size_t ring = depth + ahead + look;               // workspaces: `depth` chunks in stage B, the rest in front of it
     std::unique_ptr<Stager> stager;
     if (any_pageable) {
         size_t bytes = 0;
@@ -1479,10 +1483,10 @@ static mdb_status run_pipeline(const mdb_deconvoluter &dc, const std::vector<Hos
     }
     // Chunk size: starts at chunk_size_for() and, unless pinned by MDB_CHUNK_SPECTRA, is re-derived
     // from the first chunk's selected-peak counts so that a chunk carries about TARGET Lorentzian
-    // evaluations (~12 ms of FP64 work): many-peak spectra get small chunks (fine-grained overlap
+    // evaluations (~6 ms of FP64 work): many-peak spectra get small chunks (fine-grained overlap
     // of kernel tails across streams), few-peak spectra get large ones (launch and smoothing
-    // latency amortised).  Measured in profiles/depth_sweep_r1_*.txt.
-    double TARGET_EVALS = 1.8e10;
+    // latency amortised).  Measured in profiles/depth_sweep_r1_*.txt and profiles/sweep_r2.txt.
+    double TARGET_EVALS = 0.9e10;
     if (const char *env = std::getenv("MDB_TARGET_EVALS")) if (std::atof(env) > 0.0) TARGET_EVALS = std::atof(env);  // sweeps
     const bool pinned_size = std::getenv("MDB_CHUNK_SPECTRA") && std::atoi(std::getenv("MDB_CHUNK_SPECTRA")) > 0;
     size_t csz = chunk_size_for(hs);
@@ -1491,8 +1495,10 @@ static mdb_status run_pipeline(const mdb_deconvoluter &dc, const std::vector<Hos
     chunks.reserve(n_spectra / 16 + 2);
     auto cleanup = [&]() {
         stager.reset();  // joins the staging threads before their buffers go back to the pool
-        for (Workspace *w : wss)
-            if (w) { cudaStreamSynchronize(w->stream); release_workspace(w); }
+        // in reverse: the pool hands out the most recently released workspace first, so the next call of
+        // the same shape gives every chunk slot the workspace (and the buffer sizes) it had this time
+        for (size_t i = wss.size(); i-- > 0;)
+            if (wss[i]) { cudaStreamSynchronize(wss[i]->stream); release_workspace(wss[i]); }
     };
     size_t next_first = 0;
     // Appends the next chunk.  Its workspace is that of chunk k - ring, which is finished first.
@@ -1533,21 +1539,27 @@ static mdb_status run_pipeline(const mdb_deconvoluter &dc, const std::vector<Hos
         size_t max_n = 0;
         for (auto &h : hs) max_n = std::max(max_n, h.n);
         const size_t mem_cap = std::max<size_t>(1, ((size_t)1536 << 20) / (48 * max_n + 4096));
-        csz = std::max<size_t>(std::min<size_t>(32, mem_cap), std::min({want, (size_t)512, mem_cap}));
+        csz = std::max<size_t>(std::min<size_t>(48, mem_cap), std::min({want, (size_t)512, mem_cap}));
     };
-    st = ensure_created(look);
-    if (st == MDB_OK) st = stage_a(chunks[0], hs, dc, memory, false);
+    size_t a_next = 0;  // the next chunk whose stage A has not been queued
+    auto queue_stage_a = [&](size_t upto) -> mdb_status {  // stage A queued for chunks 0..upto (as far as the batch reaches)
+        mdb_status s2 = ensure_created(upto + look);
+        while (s2 == MDB_OK && a_next <= upto && a_next < chunks.size()) {
+            s2 = stage_a(chunks[a_next], hs, dc, memory, false);
+            ++a_next;
+        }
+        return s2;
+    };
+    st = queue_stage_a(serial ? 0 : ahead);
     for (size_t k = 0; st == MDB_OK && k < chunks.size(); ++k) {
         if (serial) {
             st = stage_b(chunks[k], hs, dc, results, true, nullptr);
             if (st == MDB_OK) st = finish_chunk(chunks[k], results, true);
             if (st == MDB_OK && k == 0) retune(chunks[0]);
-            if (st == MDB_OK) st = ensure_created(k + 1);
-            if (st == MDB_OK && k + 1 < chunks.size()) st = stage_a(chunks[k + 1], hs, dc, memory, false);
+            if (st == MDB_OK) st = queue_stage_a(k + 1);
             continue;
         }
-        st = ensure_created(k + 1 + look);  // finishes the chunks whose workspaces are needed
-        if (st == MDB_OK && k + 1 < chunks.size()) st = stage_a(chunks[k + 1], hs, dc, memory, false);
+        if (k > 0) st = queue_stage_a(k + ahead);  // finishes the chunks whose workspaces are needed
         if (st == MDB_OK) st = stage_b(chunks[k], hs, dc, results, true, nullptr);
         if (st == MDB_OK && k == 0) retune(chunks[0]);
     }
