@@ -40,6 +40,10 @@ from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
+# read by CUDA when the context is created (i.e. before torch touches the GPU): the library's
+# pipeline wants its ~10 streams on separate hardware queues (metabodecon_rust_b200/_lib.py)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))

@@ -9,6 +9,11 @@ from __future__ import annotations
 import ctypes as C
 import os
 
+# The pipeline overlaps chunks on about ten CUDA streams; CUDA maps streams onto
+# CUDA_DEVICE_MAX_CONNECTIONS hardware queues (default 8), read when the process creates its CUDA
+# context -- ask for the maximum unless the user chose a value (see csrc/api.cu, mdb_library_loaded).
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmdb200.so")
 

@@ -135,6 +135,13 @@ extern "C" mdb_status mdb_profile_read(int kernel, double *ms, uint64_t *launche
     return MDB_OK;
 }
 
+// CUDA multiplexes streams over CUDA_DEVICE_MAX_CONNECTIONS hardware queues (default 8) and streams
+// that share a queue serialise behind each other.  The variable is read when the process creates
+// its CUDA context, so ask for the maximum as soon as the library is loaded -- unless the user chose
+// a value.  (No effect when the context already exists; the pipeline then still works, with fewer
+// of its streams truly independent.)
+__attribute__((constructor)) static void mdb_library_loaded() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
+
 extern "C" uint32_t mdb_abi_version(void) { return MDB200_ABI_VERSION; }
 extern "C" void mdb_transfer_bytes(uint64_t *h2d, uint64_t *d2h)
 {
@@ -808,9 +815,16 @@ struct Chunk {
     bool stage_b_launched = false, finished = false;
     double est_evals = 0.0;            // Lorentzian evaluations of this chunk's fit + MSE kernels (from the counts)
     std::shared_ptr<StageJob> stage_job;  // pageable host rows being gathered into ws->h_stage (null: none)
+    // Streams of this chunk (null: the workspace's own).  The pipeline hands out streams from a small
+    // per-call set (PipeStreams) instead of one pair per workspace, see run_pipeline.
+    cudaStream_t s_copy = nullptr, s_a = nullptr, s_b = nullptr;
+    cudaEvent_t ev_in = nullptr;  // inputs landed (recorded on s_copy, awaited by s_a)
     // host clock (ms since the pipeline started) at which stage A was queued, the counts had arrived,
     // stage B was queued and the results had arrived; written out by MDB_TIMELINE=<file> (tools/timeline.py)
     double t_a = 0.0, t_counts = 0.0, t_b = 0.0, t_done = 0.0;
+    // the same on the GPU's clock (timeline mode only): inputs landed, smoothing done, stage A done, first
+    // stage-B kernel started, stage B done -- CUDA events, ms after the pipeline's base event
+    cudaEvent_t g_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     std::vector<ProfSpan> spans;       // per-kernel timing, resolved in finish_chunk
 };
 
@@ -893,6 +907,12 @@ static bool host_rows_pinned(const std::vector<HostSpec> &hs, size_t first, size
 }
 
 static thread_local std::chrono::steady_clock::time_point t_pipeline_origin;
+static thread_local cudaEvent_t t_timeline_base = nullptr;  // non-null: timeline mode, GPU stamps are recorded
+static void timeline_stamp(Chunk &ck, int which, cudaStream_t stream)
+{
+    if (!t_timeline_base) return;
+    if (cudaEventCreate(&ck.g_ev[which]) == cudaSuccess) cudaEventRecord(ck.g_ev[which], stream);
+}
 static double pipeline_ms()
 {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_pipeline_origin).count();
@@ -904,6 +924,12 @@ static mdb_status stage_a(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
 {
     Workspace &ws = *ck.ws;
     const size_t S = ck.count;
+    // stage A's kernels run on `sa`; the input copies go through `sc` -- ONE copy stream per pipeline, so
+    // that the chunks' H2D copies happen in chunk order (copies of different streams are interleaved by
+    // the hardware in no particular order: chunk 1's rows were seen landing after chunk 3's), and `sa`
+    // waits for them through an event
+    const cudaStream_t sa = ck.s_a ? ck.s_a : ws.stream_a;
+    const cudaStream_t sc = ck.s_copy ? ck.s_copy : sa;
     // ---- layout
     size_t y_elems = 0, cand_elems = 0, tile_elems = 0, ig_elems = 0;
     std::vector<size_t> y_off(S), cand_off(S), tile_off(S), ig_off(S);
@@ -981,16 +1007,16 @@ static mdb_status stage_a(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
         for (size_t q = 0; q < h.ig.size(); ++q) h_ig[ig_off[s] + q] = h.ig[q];
     }
     std::memcpy(ws.h_desc.p, ck.desc.data(), S * sizeof(SpecDesc));
-    CUDA_TRY(counted_memcpy_async(ws.desc.p, ws.h_desc.p, S * sizeof(SpecDesc), cudaMemcpyHostToDevice, ws.stream_a));
+    CUDA_TRY(counted_memcpy_async(ws.desc.p, ws.h_desc.p, S * sizeof(SpecDesc), cudaMemcpyHostToDevice, sc));
     if (ig_elems)
-        CUDA_TRY(counted_memcpy_async(ws.ig.p, ws.h_ig.p, ig_elems * 4, cudaMemcpyHostToDevice, ws.stream_a));
+        CUDA_TRY(counted_memcpy_async(ws.ig.p, ws.h_ig.p, ig_elems * 4, cudaMemcpyHostToDevice, sc));
 
     // ---- inputs to the device (rows that are adjacent on the host and on the device go as one copy)
     double *y_dst = skip_smoothing_input_is_smoothed ? ws.ys.as<double>() : ws.y.as<double>();
     if (memory == MDB_MEM_HOST) {
         for (auto &kv : x_map)
             CUDA_TRY(counted_memcpy_async(ws.x.as<double>() + kv.second, kv.first.first, kv.first.second * 8,
-                                          cudaMemcpyHostToDevice, ws.stream_a));
+                                          cudaMemcpyHostToDevice, sc));
         if (ck.stage_job) {
             // pageable rows, gathered ahead of time by the staging threads (prepare_staging): one DMA per part
             StageJob &job = *ck.stage_job;
@@ -999,7 +1025,7 @@ static mdb_status stage_a(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
                 job.wait_part(pt);
                 const size_t row1 = job.part_end[pt];
                 const size_t e0 = y_off[row0], e1 = row1 < S ? y_off[row1] : y_elems;
-                CUDA_TRY(counted_memcpy_async(y_dst + e0, job.dst + e0, (e1 - e0) * 8, cudaMemcpyHostToDevice, ws.stream_a));
+                CUDA_TRY(counted_memcpy_async(y_dst + e0, job.dst + e0, (e1 - e0) * 8, cudaMemcpyHostToDevice, sc));
                 row0 = row1;
             }
             ck.stage_job.reset();
@@ -1007,10 +1033,10 @@ static mdb_status stage_a(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
             // pageable rows of a single-chunk entry point (the stage_* functions): gather on this thread
             CUDA_TRY(ws.h_stage.ensure(y_elems * 8));
             double *stage = ws.h_stage.as<double>();
-            CUDA_TRY(cudaStreamSynchronize(ws.stream_a));  // the previous DMA out of this staging area has finished
+            CUDA_TRY(cudaStreamSynchronize(sc));  // the previous DMA out of this staging area has finished
             for (size_t s = 0; s < S; ++s)
                 std::memcpy(stage + y_off[s], hs[ck.first + s].y, hs[ck.first + s].n * 8);
-            CUDA_TRY(counted_memcpy_async(y_dst, stage, y_elems * 8, cudaMemcpyHostToDevice, ws.stream_a));
+            CUDA_TRY(counted_memcpy_async(y_dst, stage, y_elems * 8, cudaMemcpyHostToDevice, sc));
         } else {
             size_t s = 0;
             while (s < S) {
@@ -1022,7 +1048,7 @@ static mdb_status stage_a(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
                     if (hp.n % 16 == 0 && hn.y == hp.y + hp.n) { bytes += hn.n * 8; ++e; }
                     else break;
                 }
-                cudaError_t ce = counted_memcpy_async(y_dst + y_off[s], h0.y, bytes, cudaMemcpyHostToDevice, ws.stream_a);
+                cudaError_t ce = counted_memcpy_async(y_dst + y_off[s], h0.y, bytes, cudaMemcpyHostToDevice, sc);
                 if (ce == cudaErrorInvalidValue && e > s + 1) {
                     // adjacent in the address space but not one page-locked allocation (separately allocated
                     // rows that happen to touch): a copy may not span two allocations -- row by row instead
@@ -1030,7 +1056,7 @@ static mdb_status stage_a(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
                     g_h2d_bytes -= bytes;
                     for (size_t q = s; q < e; ++q)
                         CUDA_TRY(counted_memcpy_async(y_dst + y_off[q], hs[ck.first + q].y, hs[ck.first + q].n * 8,
-                                                      cudaMemcpyHostToDevice, ws.stream_a));
+                                                      cudaMemcpyHostToDevice, sc));
                 } else {
                     CUDA_TRY(ce);
                 }
@@ -1040,31 +1066,37 @@ static mdb_status stage_a(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
     } else if (skip_smoothing_input_is_smoothed) {
         for (size_t s = 0; s < S; ++s)
             CUDA_TRY(counted_memcpy_async(y_dst + y_off[s], hs[ck.first + s].y, hs[ck.first + s].n * 8,
-                                     cudaMemcpyDeviceToDevice, ws.stream_a));
+                                     cudaMemcpyDeviceToDevice, sc));
     }
 
     const SpecDesc *d_desc = ws.desc.as<SpecDesc>();
+    if (sc != sa) {  // hand over from the copy stream to this chunk's stage-A stream
+        CUDA_TRY(cudaEventRecord(ck.ev_in, sc));
+        CUDA_TRY(cudaStreamWaitEvent(sa, ck.ev_in, 0));
+    }
+    timeline_stamp(ck, 0, sa);
     // ---- K1 smoothing (deconvoluter.rs:531-532)
     if (!skip_smoothing_input_is_smoothed && !preset) {
         if (ma) {
-            mdb_status sst = launch_smooth(ws.stream_a, d_desc, ck.desc, (int)dc.smoothing.iterations,
+            mdb_status sst = launch_smooth(sa, d_desc, ck.desc, (int)dc.smoothing.iterations,
                                            (int)dc.smoothing.window_size, &ck.spans);
             if (sst != MDB_OK) return sst;
         } else {  // Identity (smoothing/identity.rs): the smoothed copy is the input itself
             for (size_t s = 0; s < S; ++s)
                 CUDA_TRY(counted_memcpy_async(ck.desc[s].ys, ck.desc[s].y, (size_t)ck.desc[s].n * 8,
-                                         cudaMemcpyDeviceToDevice, ws.stream_a));
+                                         cudaMemcpyDeviceToDevice, sa));
         }
     }
+    timeline_stamp(ck, 1, sa);
     // ---- K2/K3 detection + scoring
     {
         dim3 grid((unsigned)((ck.max_tiles + DETECT_WARPS - 1) / DETECT_WARPS), (unsigned)S);
         double pts = 0.0;
         for (size_t s = 0; s < S; ++s) pts += (double)ck.desc[s].n;
-        prof_begin(&ck.spans, MDB_KERNEL_DETECT, ws.stream_a);
-        detect_kernel<<<grid, DETECT_THREADS, 0, ws.stream_a>>>(d_desc);
+        prof_begin(&ck.spans, MDB_KERNEL_DETECT, sa);
+        detect_kernel<<<grid, DETECT_THREADS, 0, sa>>>(d_desc);
         LAUNCH_CHECK();
-        prof_end(&ck.spans, ws.stream_a, 8.0 * pts);  // algorithmic bytes: read 8N
+        prof_end(&ck.spans, sa, 8.0 * pts);  // algorithmic bytes: read 8N
     }
     // ---- K4 selection
     {
@@ -1075,13 +1107,20 @@ static mdb_status stage_a(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
         auto kern = few ? select_kernel<1024> : select_kernel<SELECT_THREADS>;
         if (smem > 40 * 1024)
             CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        prof_begin(&ck.spans, MDB_KERNEL_SELECT, ws.stream_a);
-        kern<<<(unsigned)S, few ? 1024 : SELECT_THREADS, smem, ws.stream_a>>>(d_desc, ws.sel_out.as<SelectOut>(), dc.selection.kind);
+        prof_begin(&ck.spans, MDB_KERNEL_SELECT, sa);
+        // MDB_ZEROCOPY_COUNTS=1 (experiment): the kernel stores the counts straight into the mapped pinned
+        // buffer instead of a D2H copy behind it
+        static const bool zero_copy_counts = std::getenv("MDB_ZEROCOPY_COUNTS") && std::getenv("MDB_ZEROCOPY_COUNTS")[0] == '1';
+        SelectOut *so_dst = ws.sel_out.as<SelectOut>();
+        if (zero_copy_counts) CUDA_TRY(cudaHostGetDevicePointer((void **)&so_dst, ws.h_sel_out.p, 0));
+        kern<<<(unsigned)S, few ? 1024 : SELECT_THREADS, smem, sa>>>(d_desc, so_dst, dc.selection.kind);
         LAUNCH_CHECK();
-        prof_end(&ck.spans, ws.stream_a, (double)S);
+        prof_end(&ck.spans, sa, (double)S);
+        if (zero_copy_counts) count_transfer(S * sizeof(SelectOut), cudaMemcpyDeviceToHost);
+        else CUDA_TRY(counted_memcpy_async(ws.h_sel_out.p, ws.sel_out.p, S * sizeof(SelectOut), cudaMemcpyDeviceToHost, sa));
     }
-    CUDA_TRY(counted_memcpy_async(ws.h_sel_out.p, ws.sel_out.p, S * sizeof(SelectOut), cudaMemcpyDeviceToHost, ws.stream_a));
-    CUDA_TRY(cudaEventRecord(ws.ev_a, ws.stream_a));
+    CUDA_TRY(cudaEventRecord(ws.ev_a, sa));
+    timeline_stamp(ck, 2, sa);
     ck.t_a = pipeline_ms();
     return MDB_OK;
 }
@@ -1103,8 +1142,10 @@ static mdb_status stage_b(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
 {
     Workspace &ws = *ck.ws;
     const size_t S = ck.count;
+    const cudaStream_t sb = ck.s_b ? ck.s_b : ws.stream;
     CUDA_TRY(cudaEventSynchronize(ws.ev_a));
     ck.t_counts = pipeline_ms();
+    timeline_stamp(ck, 3, sb);
     const SelectOut *so = ws.h_sel_out.as<SelectOut>();
     ck.fdesc.assign(S, FitDesc{});
     ck.segs.clear();
@@ -1175,10 +1216,10 @@ static mdb_status stage_b(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
     CUDA_TRY(ws.h_n_kept.ensure(S * 4));
     CUDA_TRY(ws.h_mse.ensure(S * 8));
     std::memcpy(ws.h_fdesc.p, ck.fdesc.data(), S * sizeof(FitDesc));
-    CUDA_TRY(counted_memcpy_async(ws.fdesc.p, ws.h_fdesc.p, S * sizeof(FitDesc), cudaMemcpyHostToDevice, ws.stream));
+    CUDA_TRY(counted_memcpy_async(ws.fdesc.p, ws.h_fdesc.p, S * sizeof(FitDesc), cudaMemcpyHostToDevice, sb));
     if (n_seg) {
         std::memcpy(ws.h_segs.p, ck.segs.data(), n_seg * sizeof(Segment));
-        CUDA_TRY(counted_memcpy_async(ws.segs.p, ws.h_segs.p, n_seg * sizeof(Segment), cudaMemcpyHostToDevice, ws.stream));
+        CUDA_TRY(counted_memcpy_async(ws.segs.p, ws.h_segs.p, n_seg * sizeof(Segment), cudaMemcpyHostToDevice, sb));
     }
     const SpecDesc *d_desc = ws.desc.as<SpecDesc>();
     const FitDesc *d_fd = ws.fdesc.as<FitDesc>();
@@ -1188,14 +1229,14 @@ static mdb_status stage_b(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
     for (size_t s = 0; s < S; ++s) iters = std::max(iters, ck.fdesc[s].n_peaks > 0 ? ck.fdesc[s].n_iters : 0);
     if (ck.p_total > 0) {
         dim3 grid((unsigned)((ck.max_peaks + FIT_THREADS - 1) / FIT_THREADS), (unsigned)S);
-        prof_begin(&ck.spans, MDB_KERNEL_FIT_INIT, ws.stream);
-        fit_init_kernel<<<grid, FIT_THREADS, 0, ws.stream>>>(d_desc, d_fd, st, ws.peaks_dense.as<int>());
+        prof_begin(&ck.spans, MDB_KERNEL_FIT_INIT, sb);
+        fit_init_kernel<<<grid, FIT_THREADS, 0, sb>>>(d_desc, d_fd, st, ws.peaks_dense.as<int>());
         LAUNCH_CHECK();
-        prof_end(&ck.spans, ws.stream, (double)ck.p_total);
+        prof_end(&ck.spans, sb, (double)ck.p_total);
         // trace is a single-spectrum facility (mdb_stage_fit): p_total carries alignment padding, n_peaks does not
         const size_t n_trace = (size_t)ck.fdesc[0].n_peaks;
         if (trace) {
-            CUDA_TRY(counted_memcpy_async(trace, st.pa, n_trace * 24, cudaMemcpyDeviceToHost, ws.stream));
+            CUDA_TRY(counted_memcpy_async(trace, st.pa, n_trace * 24, cudaMemcpyDeviceToHost, sb));
         }
         // Default: one launch per refinement pass.  MDB_FIT_PERSISTENT=1 selects the single-launch
         // work-queue form (fit_persistent_kernel); measured 10 % slower per chunk and 6.5 % slower end
@@ -1227,20 +1268,20 @@ static mdb_status stage_b(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
                 double evals = 0.0;
                 for (size_t s = 0; s < S; ++s)
                     if (it < ck.fdesc[s].n_iters) evals += 3.0 * (double)ck.fdesc[s].n_peaks * (double)ck.fdesc[s].n_peaks;
-                prof_begin(&ck.spans, MDB_KERNEL_FIT_ITER, ws.stream);
+                prof_begin(&ck.spans, MDB_KERNEL_FIT_ITER, sb);
                 if (wide2) {
                     dim3 g2((unsigned)((ck.max_peaks + WIDE2_CHAINS - 1) / WIDE2_CHAINS), (unsigned)S, 3);
-                    fit_wide2_superpose_kernel<<<g2, WIDE2_THREADS, WIDE2_SMEM, ws.stream>>>(d_fd, st, yn, yn_stride, it);
+                    fit_wide2_superpose_kernel<<<g2, WIDE2_THREADS, WIDE2_SMEM, sb>>>(d_fd, st, yn, yn_stride, it);
                 } else {
-                    fit_wide_superpose_kernel<<<grid3, FIT_THREADS, LOR_SMEM_BYTES, ws.stream>>>(d_fd, st, yn, yn_stride, it);
+                    fit_wide_superpose_kernel<<<grid3, FIT_THREADS, LOR_SMEM_BYTES, sb>>>(d_fd, st, yn, yn_stride, it);
                 }
                 LAUNCH_CHECK();
-                fit_wide_solve_kernel<<<grid, FIT_THREADS, 0, ws.stream>>>(d_fd, st, yn, yn_stride, it);
+                fit_wide_solve_kernel<<<grid, FIT_THREADS, 0, sb>>>(d_fd, st, yn, yn_stride, it);
                 LAUNCH_CHECK();
-                prof_end(&ck.spans, ws.stream, evals);
+                prof_end(&ck.spans, sb, evals);
                 if (trace)
                     CUDA_TRY(counted_memcpy_async(trace + (size_t)(it + 1) * n_trace, (it & 1) ? st.pa : st.pb, n_trace * 24,
-                                             cudaMemcpyDeviceToHost, ws.stream));
+                                             cudaMemcpyDeviceToHost, sb));
             }
         } else if (trace || !(persistent && persistent[0] == '1')) {
             // one launch per refinement pass (needed for the per-pass trace of mdb_stage_fit)
@@ -1248,14 +1289,14 @@ static mdb_status stage_b(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
                 double evals = 0.0;  // E_fit of this pass = sum of 3 * P_s^2 over the spectra still iterating
                 for (size_t s = 0; s < S; ++s)
                     if (it < ck.fdesc[s].n_iters) evals += 3.0 * (double)ck.fdesc[s].n_peaks * (double)ck.fdesc[s].n_peaks;
-                prof_begin(&ck.spans, MDB_KERNEL_FIT_ITER, ws.stream);
+                prof_begin(&ck.spans, MDB_KERNEL_FIT_ITER, sb);
                 auto fit_kern = dc.fit_arith == MDB_FIT_ULP ? fit_iter_kernel<2> : dc.fit_arith == MDB_FIT_CORRECTED ? fit_iter_kernel<3> : fit_iter_kernel<1>;
-                fit_kern<<<grid, FIT_THREADS, LOR_SMEM_BYTES, ws.stream>>>(d_fd, st, it);
+                fit_kern<<<grid, FIT_THREADS, LOR_SMEM_BYTES, sb>>>(d_fd, st, it);
                 LAUNCH_CHECK();
-                prof_end(&ck.spans, ws.stream, evals);
+                prof_end(&ck.spans, sb, evals);
                 if (trace)
                     CUDA_TRY(counted_memcpy_async(trace + (size_t)(it + 1) * n_trace, (it & 1) ? st.pa : st.pb, n_trace * 24,
-                                             cudaMemcpyDeviceToHost, ws.stream));
+                                             cudaMemcpyDeviceToHost, sb));
             }
         } else if (iters > 0) {
             // all passes in ONE persistent launch: work items through an atomic queue, per-(spectrum,
@@ -1272,8 +1313,8 @@ static mdb_status stage_b(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
             const int blocks_per_pass = h_blk[S];
             const size_t n_counters = 1 + S * (size_t)iters;
             CUDA_TRY(ws.fit_queue.ensure(n_counters * 4));
-            CUDA_TRY(counted_memcpy_async(ws.blk_off.p, ws.h_blk_off.p, (S + 1) * 4, cudaMemcpyHostToDevice, ws.stream));
-            CUDA_TRY(cudaMemsetAsync(ws.fit_queue.p, 0, n_counters * 4, ws.stream));
+            CUDA_TRY(counted_memcpy_async(ws.blk_off.p, ws.h_blk_off.p, (S + 1) * 4, cudaMemcpyHostToDevice, sb));
+            CUDA_TRY(cudaMemsetAsync(ws.fit_queue.p, 0, n_counters * 4, sb));
             FitQueue q;
             q.next_item = ws.fit_queue.as<int>();
             q.done = ws.fit_queue.as<int>() + 1;
@@ -1284,47 +1325,48 @@ static mdb_status stage_b(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
             const long long items = (long long)blocks_per_pass * iters;
             const unsigned pgrid = (unsigned)std::min<long long>(items, (long long)sm_count() * 8);
             if (pgrid > 0) {
-                prof_begin(&ck.spans, MDB_KERNEL_FIT_ITER, ws.stream);
-                fit_persistent_kernel<<<pgrid, FIT_THREADS, LOR_SMEM_BYTES, ws.stream>>>(d_fd, st, q);
+                prof_begin(&ck.spans, MDB_KERNEL_FIT_ITER, sb);
+                fit_persistent_kernel<<<pgrid, FIT_THREADS, LOR_SMEM_BYTES, sb>>>(d_fd, st, q);
                 LAUNCH_CHECK();
-                prof_end(&ck.spans, ws.stream, evals);
+                prof_end(&ck.spans, sb, evals);
             }
         }
     }
-    prof_begin(&ck.spans, MDB_KERNEL_RETAIN, ws.stream);
-    retain_kernel<<<(unsigned)S, RETAIN_THREADS, 0, ws.stream>>>(d_fd, st.pa, st.pb, ws.lor.as<double>(), ws.n_kept.as<int>());
+    prof_begin(&ck.spans, MDB_KERNEL_RETAIN, sb);
+    retain_kernel<<<(unsigned)S, RETAIN_THREADS, 0, sb>>>(d_fd, st.pa, st.pb, ws.lor.as<double>(), ws.n_kept.as<int>());
     LAUNCH_CHECK();
-    prof_end(&ck.spans, ws.stream, (double)ck.p_total);
+    prof_end(&ck.spans, sb, (double)ck.p_total);
     if (with_mse && n_seg) {
         const int r = sup_r;
         dim3 grid((unsigned)((ck.max_seg_len + per_block - 1) / per_block), (unsigned)n_seg);
         if (grid.x > 0) {
-            prof_begin(&ck.spans, MDB_KERNEL_MSE_SUPERPOSITION, ws.stream);
+            prof_begin(&ck.spans, MDB_KERNEL_MSE_SUPERPOSITION, sb);
             auto kern = ulp ? (r == 16 ? superposition_kernel<2, 16, 2> : r == 8 ? superposition_kernel<2, 8, 2> : superposition_kernel<2, 2, 2>)
                             : (r == 8 ? superposition_kernel<1, 8, 1> : superposition_kernel<1, 2, 1>);
-            kern<<<grid, SUP_THREADS, LOR_SMEM_BYTES, ws.stream>>>(nullptr, 0, nullptr, 0, ws.resid.as<double>(), d_desc, d_fd,
+            kern<<<grid, SUP_THREADS, LOR_SMEM_BYTES, sb>>>(nullptr, 0, nullptr, 0, ws.resid.as<double>(), d_desc, d_fd,
                                                                   ws.segs.as<Segment>(), ws.lor.as<double>(),
                                                                   ws.n_kept.as<int>());
             LAUNCH_CHECK();
-            prof_end(&ck.spans, ws.stream, -1.0);  // work = sum(points * kept), known in finish_chunk
+            prof_end(&ck.spans, sb, -1.0);  // work = sum(points * kept), known in finish_chunk
         }
-        prof_begin(&ck.spans, MDB_KERNEL_MSE_REDUCE, ws.stream);
+        prof_begin(&ck.spans, MDB_KERNEL_MSE_REDUCE, sb);
         if (ulp)  // few-ulp mode: fold the CTA sums K7 left behind (mse_partials_kernel)
-            mse_partials_kernel<<<(unsigned)((S + MSE_PART_WARPS - 1) / MSE_PART_WARPS), 32 * MSE_PART_WARPS, 0, ws.stream>>>(
+            mse_partials_kernel<<<(unsigned)((S + MSE_PART_WARPS - 1) / MSE_PART_WARPS), 32 * MSE_PART_WARPS, 0, sb>>>(
                 d_fd, ws.segs.as<Segment>(), ws.resid.as<double>(), ws.mse.as<double>(), (int)S, per_block);
         else
-            mse_reduce_kernel<<<(unsigned)((S + MSE_WARPS - 1) / MSE_WARPS), 32 * MSE_WARPS, 0, ws.stream>>>(d_fd, ws.segs.as<Segment>(),
+            mse_reduce_kernel<<<(unsigned)((S + MSE_WARPS - 1) / MSE_WARPS), 32 * MSE_WARPS, 0, sb>>>(d_fd, ws.segs.as<Segment>(),
                                                                                   ws.resid.as<double>(), ws.mse.as<double>(), (int)S);
         LAUNCH_CHECK();
-        prof_end(&ck.spans, ws.stream, 8.0 * (double)ck.res_total);
-        CUDA_TRY(counted_memcpy_async(ws.h_mse.p, ws.mse.p, S * 8, cudaMemcpyDeviceToHost, ws.stream));
+        prof_end(&ck.spans, sb, 8.0 * (double)ck.res_total);
+        CUDA_TRY(counted_memcpy_async(ws.h_mse.p, ws.mse.p, S * 8, cudaMemcpyDeviceToHost, sb));
     }
-    CUDA_TRY(counted_memcpy_async(ws.h_n_kept.p, ws.n_kept.p, S * 4, cudaMemcpyDeviceToHost, ws.stream));
+    CUDA_TRY(counted_memcpy_async(ws.h_n_kept.p, ws.n_kept.p, S * 4, cudaMemcpyDeviceToHost, sb));
     if (ck.p_total > 0) {
-        CUDA_TRY(counted_memcpy_async(ws.h_lor.p, ws.lor.p, (size_t)ck.p_total * 24, cudaMemcpyDeviceToHost, ws.stream));
-        CUDA_TRY(counted_memcpy_async(ws.h_peaks.p, ws.peaks_dense.p, (size_t)ck.p_total * 12, cudaMemcpyDeviceToHost, ws.stream));
+        CUDA_TRY(counted_memcpy_async(ws.h_lor.p, ws.lor.p, (size_t)ck.p_total * 24, cudaMemcpyDeviceToHost, sb));
+        CUDA_TRY(counted_memcpy_async(ws.h_peaks.p, ws.peaks_dense.p, (size_t)ck.p_total * 12, cudaMemcpyDeviceToHost, sb));
     }
-    CUDA_TRY(cudaEventRecord(ws.ev_b, ws.stream));
+    CUDA_TRY(cudaEventRecord(ws.ev_b, sb));
+    timeline_stamp(ck, 4, sb);
     ck.stage_b_launched = true;
     ck.t_b = pipeline_ms();
     return MDB_OK;
@@ -1417,6 +1459,54 @@ static mdb_status build_host_specs(const mdb_deconvoluter &dc, const mdb_spectru
     return MDB_OK;
 }
 
+// The streams of one pipeline call.  CUDA multiplexes streams over a small number of hardware queues
+// (CUDA_DEVICE_MAX_CONNECTIONS, 8 unless the process raised it before creating its context); streams
+// that share a queue serialise behind each other, which was measured as stage B of chunk k+2 starting
+// only when chunk k had finished with one stream pair per workspace (22 streams).  So a call uses a
+// small fixed set, handed to the chunks round robin: ONE copy stream (input copies in chunk order),
+// N_A high-priority stage-A streams, and `depth` low-priority stage-B streams.
+struct PipeStreams {
+    static constexpr int MAX_A = 4, MAX_B = 32;
+    int device = -1;
+    cudaStream_t copy = nullptr, a[MAX_A] = {}, b[MAX_B] = {};
+    cudaEvent_t ev_in[64] = {};  // "inputs landed", one per workspace slot of the ring
+};
+static std::mutex g_pipe_mutex;
+static std::multimap<int, PipeStreams *> g_pipe_pool;
+
+static mdb_status acquire_pipe_streams(PipeStreams **out)
+{
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    {
+        std::lock_guard<std::mutex> lock(g_pipe_mutex);
+        auto it = g_pipe_pool.find(dev);
+        if (it != g_pipe_pool.end()) {
+            *out = it->second;
+            g_pipe_pool.erase(it);
+            return MDB_OK;
+        }
+    }
+    auto *ps = new PipeStreams();
+    ps->device = dev;
+    int least = 0, greatest = 0;
+    CUDA_TRY(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    if (const char *env = std::getenv("MDB_STREAM_PRIORITIES")) if (env[0] == '0') greatest = least;  // measurement aid
+    CUDA_TRY(cudaStreamCreateWithPriority(&ps->copy, cudaStreamNonBlocking, greatest));
+    for (auto &st : ps->a) CUDA_TRY(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, greatest));
+    for (auto &st : ps->b) CUDA_TRY(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, least));
+    for (auto &e : ps->ev_in) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    *out = ps;
+    return MDB_OK;
+}
+
+static void release_pipe_streams(PipeStreams *ps)
+{
+    if (!ps) return;
+    std::lock_guard<std::mutex> lock(g_pipe_mutex);
+    g_pipe_pool.emplace(ps->device, ps);
+}
+
 // Submit the gather of a chunk's pageable rows into its workspace's page-locked staging area.
 static mdb_status prepare_staging(Chunk &ck, const std::vector<HostSpec> &hs, Stager &stager)
 {
@@ -1457,7 +1547,9 @@ static mdb_status run_pipeline(const mdb_deconvoluter &dc, const std::vector<Hos
     const size_t n_spectra = hs.size();
     mdb_status st = MDB_OK;
     t_pipeline_origin = std::chrono::steady_clock::now();
-    size_t depth = 8;
+    t_timeline_base = nullptr;
+    if (std::getenv("MDB_TIMELINE") && cudaEventCreate(&t_timeline_base) == cudaSuccess) cudaEventRecord(t_timeline_base, nullptr);
+    size_t depth = 6;  // chunks in stage B at a time = stage-B streams (sweeps: profiles/sweep_r2.txt)
     if (const char *env = std::getenv("MDB_PIPELINE_DEPTH"))
         if (std::atoi(env) >= 1) depth = (size_t)std::min(std::atoi(env), 32);
     // Pageable rows?  (probed on the first and the last spectrum; a chunk that mixes kinds is still
@@ -1493,7 +1585,18 @@ static mdb_status run_pipeline(const mdb_deconvoluter &dc, const std::vector<Hos
     std::vector<Workspace *> wss;
     std::vector<Chunk> chunks;
     chunks.reserve(n_spectra / 16 + 2);
+    PipeStreams *pipe = nullptr;
+    if ((st = acquire_pipe_streams(&pipe)) != MDB_OK) return st;
+    size_t n_a = 2;  // stage-A streams: two chunks' smoothing / detection / selection side by side
+    if (const char *env = std::getenv("MDB_STAGE_A_STREAMS")) if (std::atoi(env) >= 1) n_a = (size_t)std::min(std::atoi(env), (int)PipeStreams::MAX_A);
     auto cleanup = [&]() {
+        if (pipe) {
+            cudaStreamSynchronize(pipe->copy);
+            for (size_t i = 0; i < n_a; ++i) cudaStreamSynchronize(pipe->a[i]);
+            for (size_t i = 0; i < depth; ++i) cudaStreamSynchronize(pipe->b[i]);
+            release_pipe_streams(pipe);
+            pipe = nullptr;
+        }
         stager.reset();  // joins the staging threads before their buffers go back to the pool
         // in reverse: the pool hands out the most recently released workspace first, so the next call of
         // the same shape gives every chunk slot the workspace (and the buffer sizes) it had this time
@@ -1516,6 +1619,10 @@ static mdb_status run_pipeline(const mdb_deconvoluter &dc, const std::vector<Hos
         }
         Chunk ck;
         ck.ws = wss[k % ring];
+        ck.s_copy = pipe->copy;
+        ck.s_a = pipe->a[k % n_a];
+        ck.s_b = pipe->b[k % depth];
+        ck.ev_in = pipe->ev_in[k % ring];
         ck.first = next_first;
         size_t count = std::min(csz, n_spectra - next_first);
         if (n_spectra - next_first - count < csz / 4) count = n_spectra - next_first;  // no tiny straggler chunk
@@ -1572,13 +1679,24 @@ static mdb_status run_pipeline(const mdb_deconvoluter &dc, const std::vector<Hos
             int dev = 0;
             cudaGetDevice(&dev);
             std::fprintf(f, "{\"device\": %d, \"spectra\": %zu, \"total_ms\": %.3f, \"chunks\": [", dev, n_spectra, pipeline_ms());
-            for (size_t k = 0; k < chunks.size(); ++k)
-                std::fprintf(f, "%s[%zu, %zu, %.3f, %.3f, %.3f, %.3f]", k ? ", " : "", chunks[k].first, chunks[k].count,
-                             chunks[k].t_a, chunks[k].t_counts, chunks[k].t_b, chunks[k].t_done);
+            for (size_t k = 0; k < chunks.size(); ++k) {
+                float g[5] = {-1.f, -1.f, -1.f, -1.f, -1.f};
+                for (int q = 0; q < 5; ++q)
+                    if (t_timeline_base && chunks[k].g_ev[q] && cudaEventElapsedTime(&g[q], t_timeline_base, chunks[k].g_ev[q]) != cudaSuccess) {
+                        cudaGetLastError();
+                        g[q] = -1.f;
+                    }
+                std::fprintf(f, "%s[%zu, %zu, %.3f, %.3f, %.3f, %.3f, %.3f, %.3f, %.3f, %.3f, %.3f]", k ? ", " : "", chunks[k].first,
+                             chunks[k].count, chunks[k].t_a, chunks[k].t_counts, chunks[k].t_b, chunks[k].t_done, g[0], g[1], g[2], g[3], g[4]);
+            }
             std::fprintf(f, "]}\n");
             std::fclose(f);
         }
     }
+    for (Chunk &ck : chunks)
+        for (cudaEvent_t &e : ck.g_ev)
+            if (e) { cudaEventDestroy(e); e = nullptr; }
+    if (t_timeline_base) { cudaEventDestroy(t_timeline_base); t_timeline_base = nullptr; }
     cleanup();
     return st;
 }

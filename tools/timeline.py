@@ -72,10 +72,13 @@ def main():
     r = runs[best]
     print(f"# {args.workload}, {S} spectra, {args.memory} inputs: call {1e3 * walls[best]:.2f} ms wall, pipeline {r['total_ms']:.2f} ms "
           f"= {S / (walls[best]):.0f} spectra/s; all walls (ms): {[round(1e3 * w, 2) for w in walls]}")
-    print("# chunk first count | stage A queued | counts on host | stage B queued | results on host   (ms since the call started)")
-    for i, (first, count, ta, tc, tb, td) in enumerate(r["chunks"]):
-        print(f"{i:4d} {first:6d} {count:5d} | {ta:9.2f} | {tc:9.2f} | {tb:9.2f} | {td:9.2f}")
-    ch = r["chunks"]
+    print("# host clock: stage A queued | counts on host | stage B queued | results on host;  GPU clock: inputs landed | smoothed | stage A done | stage B starts | stage B done   (ms since the call started)")
+    print("# chunk first count |  A queued |    counts |  B queued |   results ||    inputs |  smoothed |    A done |   B start |    B done")
+    for i, row in enumerate(r["chunks"]):
+        first, count, ta, tc, tb, td = row[:6]
+        g = row[6:] if len(row) > 6 else [-1] * 5
+        print(f"{i:4d} {first:6d} {count:5d} | {ta:9.2f} | {tc:9.2f} | {tb:9.2f} | {td:9.2f} || " + " | ".join(f"{v:9.2f}" for v in g))
+    ch = [row[:6] for row in r["chunks"]]
     steady = [(ch[i + 1][5] - ch[i][5]) / ch[i + 1][1] for i in range(len(ch) // 3, len(ch) - 2) if ch[i + 1][1]]
     if steady:
         per = float(np.median(steady))
