@@ -87,9 +87,15 @@ static std::mutex g_prof_mutex;
 static ProfAcc g_prof[MDB_KERNEL_COUNT];
 struct ProfSpan { int kernel; cudaEvent_t e0, e1; double work; };
 
+// Timeline mode (MDB_TIMELINE=<file>, tools/timeline.py): the spans are recorded even when per-kernel
+// profiling is off, and every span is also written out as (kernel, start, end) on the GPU's clock.
+static thread_local cudaEvent_t t_timeline_base = nullptr;  // non-null: timeline mode
+struct TraceRow { int kernel; float t0, t1; };
+static thread_local std::vector<TraceRow> t_trace;
+
 static void prof_begin(std::vector<ProfSpan> *spans, int kernel, cudaStream_t stream)
 {
-    if (!spans || !g_profile.load()) return;
+    if (!spans || !(g_profile.load() || t_timeline_base)) return;
     ProfSpan sp{kernel, nullptr, nullptr, 0.0};
     if (cudaEventCreate(&sp.e0) != cudaSuccess || cudaEventCreate(&sp.e1) != cudaSuccess) return;
     cudaEventRecord(sp.e0, stream);
@@ -97,7 +103,7 @@ static void prof_begin(std::vector<ProfSpan> *spans, int kernel, cudaStream_t st
 }
 static void prof_end(std::vector<ProfSpan> *spans, cudaStream_t stream, double work)
 {
-    if (!spans || !g_profile.load() || spans->empty()) return;
+    if (!spans || !(g_profile.load() || t_timeline_base) || spans->empty()) return;
     ProfSpan &sp = spans->back();
     sp.work = work;
     cudaEventRecord(sp.e1, stream);
@@ -109,7 +115,15 @@ static void prof_resolve(std::vector<ProfSpan> *spans)
     std::lock_guard<std::mutex> lock(g_prof_mutex);
     for (ProfSpan &sp : *spans) {
         float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, sp.e0, sp.e1) == cudaSuccess && sp.kernel >= 0 && sp.kernel < MDB_KERNEL_COUNT) {
+        if (t_timeline_base) {
+            TraceRow row{sp.kernel, -1.f, -1.f};
+            if (cudaEventElapsedTime(&row.t0, t_timeline_base, sp.e0) == cudaSuccess
+                && cudaEventElapsedTime(&row.t1, t_timeline_base, sp.e1) == cudaSuccess)
+                t_trace.push_back(row);
+            else
+                cudaGetLastError();
+        }
+        if (g_profile.load() && cudaEventElapsedTime(&ms, sp.e0, sp.e1) == cudaSuccess && sp.kernel >= 0 && sp.kernel < MDB_KERNEL_COUNT) {
             g_prof[sp.kernel].ms += ms;
             g_prof[sp.kernel].launches += 1;
             g_prof[sp.kernel].work += sp.work;
@@ -744,6 +758,12 @@ struct StageJob {
         std::unique_lock<std::mutex> lk(m);
         cv.wait(lk, [&] { return part_left[p].load() == 0; });
     }
+    bool all_done() const
+    {
+        for (size_t p = 0; p < part_end.size(); ++p)
+            if (part_left[p].load() != 0) return false;
+        return true;
+    }
 };
 
 class Stager {
@@ -907,7 +927,6 @@ static bool host_rows_pinned(const std::vector<HostSpec> &hs, size_t first, size
 }
 
 static thread_local std::chrono::steady_clock::time_point t_pipeline_origin;
-static thread_local cudaEvent_t t_timeline_base = nullptr;  // non-null: timeline mode, GPU stamps are recorded
 static void timeline_stamp(Chunk &ck, int which, cudaStream_t stream)
 {
     if (!t_timeline_base) return;
@@ -1215,11 +1234,22 @@ static mdb_status stage_b(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
     CUDA_TRY(ws.h_peaks.ensure(P * 12));
     CUDA_TRY(ws.h_n_kept.ensure(S * 4));
     CUDA_TRY(ws.h_mse.ensure(S * 8));
+    // The two descriptor tables go up through a tiny KERNEL that reads the page-locked host copies over
+    // PCIe (zero-copy), not through cudaMemcpyAsync: a copy command of this low-priority stream would sit
+    // in the H2D engine's queue behind hundreds of megabytes of input rows of the chunks ahead (measured:
+    // no stage-B kernel ran before the whole batch had been copied in).
     std::memcpy(ws.h_fdesc.p, ck.fdesc.data(), S * sizeof(FitDesc));
-    CUDA_TRY(counted_memcpy_async(ws.fdesc.p, ws.h_fdesc.p, S * sizeof(FitDesc), cudaMemcpyHostToDevice, sb));
-    if (n_seg) {
-        std::memcpy(ws.h_segs.p, ck.segs.data(), n_seg * sizeof(Segment));
-        CUDA_TRY(counted_memcpy_async(ws.segs.p, ws.h_segs.p, n_seg * sizeof(Segment), cudaMemcpyHostToDevice, sb));
+    if (n_seg) std::memcpy(ws.h_segs.p, ck.segs.data(), n_seg * sizeof(Segment));
+    {
+        static_assert(sizeof(FitDesc) % 8 == 0 && sizeof(Segment) % 8 == 0, "descriptor tables are copied in 8-byte words");
+        const unsigned long long *src_f = nullptr, *src_s = nullptr;
+        CUDA_TRY(cudaHostGetDevicePointer((void **)&src_f, ws.h_fdesc.p, 0));
+        CUDA_TRY(cudaHostGetDevicePointer((void **)&src_s, ws.h_segs.p, 0));
+        const size_t wf = S * sizeof(FitDesc) / 8, wsg = n_seg * sizeof(Segment) / 8;
+        upload_tables_kernel<<<(unsigned)std::min<size_t>((wf + wsg + 255) / 256, 64), 256, 0, sb>>>(
+            src_f, ws.fdesc.as<unsigned long long>(), wf, src_s, ws.segs.as<unsigned long long>(), wsg);
+        LAUNCH_CHECK();
+        count_transfer((wf + wsg) * 8, cudaMemcpyHostToDevice);
     }
     const SpecDesc *d_desc = ws.desc.as<SpecDesc>();
     const FitDesc *d_fd = ws.fdesc.as<FitDesc>();
@@ -1291,7 +1321,8 @@ static mdb_status stage_b(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
                     if (it < ck.fdesc[s].n_iters) evals += 3.0 * (double)ck.fdesc[s].n_peaks * (double)ck.fdesc[s].n_peaks;
                 prof_begin(&ck.spans, MDB_KERNEL_FIT_ITER, sb);
                 auto fit_kern = dc.fit_arith == MDB_FIT_ULP ? fit_iter_kernel<2> : dc.fit_arith == MDB_FIT_CORRECTED ? fit_iter_kernel<3> : fit_iter_kernel<1>;
-                fit_kern<<<grid, FIT_THREADS, LOR_SMEM_BYTES, sb>>>(d_fd, st, it);
+                const dim3 grid_sf((unsigned)S, grid.x);  // spectrum fastest, peak block slowest (see fit_iter_kernel)
+                fit_kern<<<grid_sf, FIT_THREADS, LOR_SMEM_BYTES, sb>>>(d_fd, st, it);
                 LAUNCH_CHECK();
                 prof_end(&ck.spans, sb, evals);
                 if (trace)
@@ -1548,6 +1579,7 @@ static mdb_status run_pipeline(const mdb_deconvoluter &dc, const std::vector<Hos
     mdb_status st = MDB_OK;
     t_pipeline_origin = std::chrono::steady_clock::now();
     t_timeline_base = nullptr;
+    t_trace.clear();
     if (std::getenv("MDB_TIMELINE") && cudaEventCreate(&t_timeline_base) == cudaSuccess) cudaEventRecord(t_timeline_base, nullptr);
     size_t depth = 6;  // chunks in stage B at a time = stage-B streams (sweeps: profiles/sweep_r2.txt)
     if (const char *env = std::getenv("MDB_PIPELINE_DEPTH"))
@@ -1649,26 +1681,37 @@ static mdb_status run_pipeline(const mdb_deconvoluter &dc, const std::vector<Hos
         csz = std::max<size_t>(std::min<size_t>(48, mem_cap), std::min({want, (size_t)512, mem_cap}));
     };
     size_t a_next = 0;  // the next chunk whose stage A has not been queued
-    auto queue_stage_a = [&](size_t upto) -> mdb_status {  // stage A queued for chunks 0..upto (as far as the batch reaches)
+    size_t b_next = 0;  // the next chunk whose stage B has not been launched
+    // Stage A queued for chunks 0..upto (as far as the batch reaches).  A chunk whose pageable rows are
+    // still being gathered is left for the next round as long as stage B has other chunks to launch:
+    // the host thread should be waiting for the GPU's counts, not for a memcpy three chunks ahead.
+    auto queue_stage_a = [&](size_t upto, bool may_defer) -> mdb_status {
         mdb_status s2 = ensure_created(upto + look);
         while (s2 == MDB_OK && a_next <= upto && a_next < chunks.size()) {
-            s2 = stage_a(chunks[a_next], hs, dc, memory, false);
+            Chunk &c = chunks[a_next];
+            if (may_defer && c.stage_job && a_next > b_next && !c.stage_job->all_done()) break;
+            s2 = stage_a(c, hs, dc, memory, false);
             ++a_next;
         }
         return s2;
     };
-    st = queue_stage_a(serial ? 0 : ahead);
+    st = queue_stage_a(serial ? 0 : ahead, false);  // the start-up burst: nothing else to do yet
     for (size_t k = 0; st == MDB_OK && k < chunks.size(); ++k) {
         if (serial) {
             st = stage_b(chunks[k], hs, dc, results, true, nullptr);
             if (st == MDB_OK) st = finish_chunk(chunks[k], results, true);
+            b_next = k + 1;
             if (st == MDB_OK && k == 0) retune(chunks[0]);
-            if (st == MDB_OK) st = queue_stage_a(k + 1);
+            if (st == MDB_OK) st = queue_stage_a(k + 1, false);
             continue;
         }
-        if (k > 0) st = queue_stage_a(k + ahead);  // finishes the chunks whose workspaces are needed
-        if (st == MDB_OK) st = stage_b(chunks[k], hs, dc, results, true, nullptr);
+        // stage B of chunk k first (its counts are usually on the host already), THEN the stage A of the chunk
+        // `ahead` in front: queueing that one may block -- on the staging threads (pageable rows) or on the
+        // chunk whose workspace it takes over -- and the FP64 kernels of chunk k should not wait for either
+        st = stage_b(chunks[k], hs, dc, results, true, nullptr);
+        b_next = k + 1;
         if (st == MDB_OK && k == 0) retune(chunks[0]);
+        if (st == MDB_OK) st = queue_stage_a(k + 1 + ahead, true);
     }
     for (size_t k = 0; st == MDB_OK && k < chunks.size(); ++k)
         if (chunks[k].stage_b_launched && !chunks[k].finished) st = finish_chunk(chunks[k], results, true);
@@ -1689,10 +1732,14 @@ static mdb_status run_pipeline(const mdb_deconvoluter &dc, const std::vector<Hos
                 std::fprintf(f, "%s[%zu, %zu, %.3f, %.3f, %.3f, %.3f, %.3f, %.3f, %.3f, %.3f, %.3f]", k ? ", " : "", chunks[k].first,
                              chunks[k].count, chunks[k].t_a, chunks[k].t_counts, chunks[k].t_b, chunks[k].t_done, g[0], g[1], g[2], g[3], g[4]);
             }
+            std::fprintf(f, "], \"kernels\": [");
+            for (size_t q = 0; q < t_trace.size(); ++q)
+                std::fprintf(f, "%s[%d, %.3f, %.3f]", q ? ", " : "", t_trace[q].kernel, t_trace[q].t0, t_trace[q].t1);
             std::fprintf(f, "]}\n");
             std::fclose(f);
         }
     }
+    t_trace.clear();
     for (Chunk &ck : chunks)
         for (cudaEvent_t &e : ck.g_ev)
             if (e) { cudaEventDestroy(e); e = nullptr; }

@@ -79,6 +79,23 @@ def main():
         g = row[6:] if len(row) > 6 else [-1] * 5
         print(f"{i:4d} {first:6d} {count:5d} | {ta:9.2f} | {tc:9.2f} | {tb:9.2f} | {td:9.2f} || " + " | ".join(f"{v:9.2f}" for v in g))
     ch = [row[:6] for row in r["chunks"]]
+    if r.get("kernels"):
+        from metabodecon_rust_b200._lib import KERNEL_NAMES
+        # GPU busy profile: per millisecond, how many kernels of each family were running (events on the launching streams)
+        end = max(k[2] for k in r["kernels"])
+        print("# kernels on the GPU clock: for every 2 ms window, the summed run time (ms) of the launches of each family that overlap it")
+        names = [n for i, n in enumerate(KERNEL_NAMES) if any(k[0] == i for k in r["kernels"])]
+        print("#   window  " + " ".join(f"{n[:12]:>12s}" for n in names))
+        t = 0.0
+        while t < end:
+            row = []
+            for n in names:
+                i = KERNEL_NAMES.index(n)
+                row.append(sum(max(0.0, min(k[2], t + 2.0) - max(k[1], t)) for k in r["kernels"] if k[0] == i))
+            print(f"# {t:5.0f}-{t + 2:<4.0f} " + " ".join(f"{v:12.2f}" for v in row))
+            t += 2.0
+        tot = {n: sum(k[2] - k[1] for k in r["kernels"] if k[0] == KERNEL_NAMES.index(n)) for n in names}
+        print("# summed launch durations (ms): " + ", ".join(f"{n} {v:.1f}" for n, v in tot.items()))
     steady = [(ch[i + 1][5] - ch[i][5]) / ch[i + 1][1] for i in range(len(ch) // 3, len(ch) - 2) if ch[i + 1][1]]
     if steady:
         per = float(np.median(steady))
