@@ -644,6 +644,8 @@ static void release_workspace(Workspace *ws)
     g_pool.emplace(ws->device, ws);
 }
 
+static void release_pipe_stream_pool(int dev);  // defined with PipeStreams below
+
 extern "C" mdb_status mdb_release_workspaces(void)
 {
     int dev = 0;
@@ -659,6 +661,7 @@ extern "C" mdb_status mdb_release_workspaces(void)
         ws->release();
         delete ws;
     }
+    release_pipe_stream_pool(dev);
     return MDB_OK;
 }
 
@@ -837,8 +840,9 @@ struct Chunk {
     std::shared_ptr<StageJob> stage_job;  // pageable host rows being gathered into ws->h_stage (null: none)
     // Streams of this chunk (null: the workspace's own).  The pipeline hands out streams from a small
     // per-call set (PipeStreams) instead of one pair per workspace, see run_pipeline.
-    cudaStream_t s_copy = nullptr, s_a = nullptr, s_b = nullptr;
-    cudaEvent_t ev_in = nullptr;  // inputs landed (recorded on s_copy, awaited by s_a)
+    cudaStream_t s_copy = nullptr, s_a = nullptr, s_b = nullptr, s_m = nullptr;
+    cudaEvent_t ev_in = nullptr;   // inputs landed (recorded on s_copy, awaited by s_a)
+    cudaEvent_t ev_fit = nullptr;  // refinement done (recorded on s_b, awaited by s_m)
     // host clock (ms since the pipeline started) at which stage A was queued, the counts had arrived,
     // stage B was queued and the results had arrived; written out by MDB_TIMELINE=<file> (tools/timeline.py)
     double t_a = 0.0, t_counts = 0.0, t_b = 0.0, t_done = 0.0;
@@ -867,6 +871,7 @@ static const DeviceInfo &device_info()
     return di;
 }
 static int smem_optin_limit() { return device_info().smem_optin; }
+constexpr int FIT_WARP_CTA_MAX = 1024;  // K6: spectra with at most this many selected peaks run one-warp CTAs
 static int sm_count() { return device_info().sms; }
 
 // K1 dispatch: the lane-per-pass TMA-staged kernel when the settings are covered (window 2..9,
@@ -1320,9 +1325,19 @@ static mdb_status stage_b(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
                 for (size_t s = 0; s < S; ++s)
                     if (it < ck.fdesc[s].n_iters) evals += 3.0 * (double)ck.fdesc[s].n_peaks * (double)ck.fdesc[s].n_peaks;
                 prof_begin(&ck.spans, MDB_KERNEL_FIT_ITER, sb);
+                // CTA shape: one warp per CTA (32 peaks, 128-Lorentzian tiles) for spectra with up to FIT_WARP_CTA_MAX
+                // peaks, 128 peaks x 512-Lorentzian tiles above (see fit_iter_kernel); MDB_FIT_CTA=32|128 forces one
+                int cta = ck.max_peaks <= FIT_WARP_CTA_MAX ? 32 : FIT_THREADS;
+                if (const char *env = std::getenv("MDB_FIT_CTA")) { const int v = std::atoi(env); if (v == 32 || v == FIT_THREADS) cta = v; }
                 auto fit_kern = dc.fit_arith == MDB_FIT_ULP ? fit_iter_kernel<2> : dc.fit_arith == MDB_FIT_CORRECTED ? fit_iter_kernel<3> : fit_iter_kernel<1>;
-                const dim3 grid_sf((unsigned)S, grid.x);  // spectrum fastest, peak block slowest (see fit_iter_kernel)
-                fit_kern<<<grid_sf, FIT_THREADS, LOR_SMEM_BYTES, sb>>>(d_fd, st, it);
+                if (cta == 32)
+                    fit_kern = dc.fit_arith == MDB_FIT_ULP ? fit_iter_kernel<2, 32, 128> : dc.fit_arith == MDB_FIT_CORRECTED ? fit_iter_kernel<3, 32, 128> : fit_iter_kernel<1, 32, 128>;
+                size_t fit_smem = cta == 32 ? fit_smem_bytes(128) : LOR_SMEM_BYTES;
+                if (const char *occ = std::getenv("MDB_FIT_OCC")) {  // experiment: 12 CTAs of 128 threads per SM (<= 40 registers, 256-Lorentzian tiles)
+                    if (occ[0] == '1' && cta == FIT_THREADS && dc.fit_arith == MDB_FIT_EXACT) { fit_kern = fit_iter_kernel<1, 128, 256, 12>; fit_smem = fit_smem_bytes(256); }
+                }
+                const dim3 grid_sf((unsigned)S, (unsigned)((ck.max_peaks + cta - 1) / cta));  // spectrum fastest, peak block slowest
+                fit_kern<<<grid_sf, cta, fit_smem, sb>>>(d_fd, st, it);
                 LAUNCH_CHECK();
                 prof_end(&ck.spans, sb, evals);
                 if (trace)
@@ -1367,37 +1382,48 @@ static mdb_status stage_b(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
     retain_kernel<<<(unsigned)S, RETAIN_THREADS, 0, sb>>>(d_fd, st.pa, st.pb, ws.lor.as<double>(), ws.n_kept.as<int>());
     LAUNCH_CHECK();
     prof_end(&ck.spans, sb, (double)ck.p_total);
+    // The MSE superposition and everything after it run on the chunk's LOWEST-priority stream `sm`, the
+    // refinement passes above on a medium-priority one: a refinement pass is a short launch the next pass
+    // waits for, K7 is one long launch with thousands of CTAs.  With both at one priority the SMs ran
+    // one kind at a time (CTAs are dispatched grid after grid); now the pending pass takes the slots
+    // that free up and K7's CTAs -- 16 independent chains per thread -- fill the FP64-pipe bubbles the
+    // three-chain refinement warps leave on the same SM.
+    const cudaStream_t sm = (ck.s_m && with_mse) ? ck.s_m : sb;
+    if (sm != sb) {
+        CUDA_TRY(cudaEventRecord(ck.ev_fit, sb));
+        CUDA_TRY(cudaStreamWaitEvent(sm, ck.ev_fit, 0));
+    }
     if (with_mse && n_seg) {
         const int r = sup_r;
         dim3 grid((unsigned)((ck.max_seg_len + per_block - 1) / per_block), (unsigned)n_seg);
         if (grid.x > 0) {
-            prof_begin(&ck.spans, MDB_KERNEL_MSE_SUPERPOSITION, sb);
+            prof_begin(&ck.spans, MDB_KERNEL_MSE_SUPERPOSITION, sm);
             auto kern = ulp ? (r == 16 ? superposition_kernel<2, 16, 2> : r == 8 ? superposition_kernel<2, 8, 2> : superposition_kernel<2, 2, 2>)
                             : (r == 8 ? superposition_kernel<1, 8, 1> : superposition_kernel<1, 2, 1>);
-            kern<<<grid, SUP_THREADS, LOR_SMEM_BYTES, sb>>>(nullptr, 0, nullptr, 0, ws.resid.as<double>(), d_desc, d_fd,
+            kern<<<grid, SUP_THREADS, LOR_SMEM_BYTES, sm>>>(nullptr, 0, nullptr, 0, ws.resid.as<double>(), d_desc, d_fd,
                                                                   ws.segs.as<Segment>(), ws.lor.as<double>(),
                                                                   ws.n_kept.as<int>());
             LAUNCH_CHECK();
-            prof_end(&ck.spans, sb, -1.0);  // work = sum(points * kept), known in finish_chunk
+            prof_end(&ck.spans, sm, -1.0);  // work = sum(points * kept), known in finish_chunk
         }
-        prof_begin(&ck.spans, MDB_KERNEL_MSE_REDUCE, sb);
+        prof_begin(&ck.spans, MDB_KERNEL_MSE_REDUCE, sm);
         if (ulp)  // few-ulp mode: fold the CTA sums K7 left behind (mse_partials_kernel)
-            mse_partials_kernel<<<(unsigned)((S + MSE_PART_WARPS - 1) / MSE_PART_WARPS), 32 * MSE_PART_WARPS, 0, sb>>>(
+            mse_partials_kernel<<<(unsigned)((S + MSE_PART_WARPS - 1) / MSE_PART_WARPS), 32 * MSE_PART_WARPS, 0, sm>>>(
                 d_fd, ws.segs.as<Segment>(), ws.resid.as<double>(), ws.mse.as<double>(), (int)S, per_block);
         else
-            mse_reduce_kernel<<<(unsigned)((S + MSE_WARPS - 1) / MSE_WARPS), 32 * MSE_WARPS, 0, sb>>>(d_fd, ws.segs.as<Segment>(),
+            mse_reduce_kernel<<<(unsigned)((S + MSE_WARPS - 1) / MSE_WARPS), 32 * MSE_WARPS, 0, sm>>>(d_fd, ws.segs.as<Segment>(),
                                                                                   ws.resid.as<double>(), ws.mse.as<double>(), (int)S);
         LAUNCH_CHECK();
-        prof_end(&ck.spans, sb, 8.0 * (double)ck.res_total);
-        CUDA_TRY(counted_memcpy_async(ws.h_mse.p, ws.mse.p, S * 8, cudaMemcpyDeviceToHost, sb));
+        prof_end(&ck.spans, sm, 8.0 * (double)ck.res_total);
+        CUDA_TRY(counted_memcpy_async(ws.h_mse.p, ws.mse.p, S * 8, cudaMemcpyDeviceToHost, sm));
     }
-    CUDA_TRY(counted_memcpy_async(ws.h_n_kept.p, ws.n_kept.p, S * 4, cudaMemcpyDeviceToHost, sb));
+    CUDA_TRY(counted_memcpy_async(ws.h_n_kept.p, ws.n_kept.p, S * 4, cudaMemcpyDeviceToHost, sm));
     if (ck.p_total > 0) {
-        CUDA_TRY(counted_memcpy_async(ws.h_lor.p, ws.lor.p, (size_t)ck.p_total * 24, cudaMemcpyDeviceToHost, sb));
-        CUDA_TRY(counted_memcpy_async(ws.h_peaks.p, ws.peaks_dense.p, (size_t)ck.p_total * 12, cudaMemcpyDeviceToHost, sb));
+        CUDA_TRY(counted_memcpy_async(ws.h_lor.p, ws.lor.p, (size_t)ck.p_total * 24, cudaMemcpyDeviceToHost, sm));
+        CUDA_TRY(counted_memcpy_async(ws.h_peaks.p, ws.peaks_dense.p, (size_t)ck.p_total * 12, cudaMemcpyDeviceToHost, sm));
     }
-    CUDA_TRY(cudaEventRecord(ws.ev_b, sb));
-    timeline_stamp(ck, 4, sb);
+    CUDA_TRY(cudaEventRecord(ws.ev_b, sm));
+    timeline_stamp(ck, 4, sm);
     ck.stage_b_launched = true;
     ck.t_b = pipeline_ms();
     return MDB_OK;
@@ -1499,8 +1525,9 @@ static mdb_status build_host_specs(const mdb_deconvoluter &dc, const mdb_spectru
 struct PipeStreams {
     static constexpr int MAX_A = 4, MAX_B = 32;
     int device = -1;
-    cudaStream_t copy = nullptr, a[MAX_A] = {}, b[MAX_B] = {};
-    cudaEvent_t ev_in[64] = {};  // "inputs landed", one per workspace slot of the ring
+    cudaStream_t copy = nullptr, a[MAX_A] = {}, b[MAX_B] = {}, m[MAX_B] = {};
+    cudaEvent_t ev_in[64] = {};   // "inputs landed", one per workspace slot of the ring
+    cudaEvent_t ev_fit[64] = {};  // "refinement done", likewise
 };
 static std::mutex g_pipe_mutex;
 static std::multimap<int, PipeStreams *> g_pipe_pool;
@@ -1525,10 +1552,38 @@ static mdb_status acquire_pipe_streams(PipeStreams **out)
     if (const char *env = std::getenv("MDB_STREAM_PRIORITIES")) if (env[0] == '0') greatest = least;  // measurement aid
     CUDA_TRY(cudaStreamCreateWithPriority(&ps->copy, cudaStreamNonBlocking, greatest));
     for (auto &st : ps->a) CUDA_TRY(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, greatest));
-    for (auto &st : ps->b) CUDA_TRY(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, least));
+    // three levels: stage A and the copies highest, the refinement passes in the middle, the MSE pass lowest
+    // -- only with MDB_FIT_PRIORITY=1; by default refinement and MSE share the lowest level and one stream per chunk
+    const char *fp = std::getenv("MDB_FIT_PRIORITY");
+    const bool split = fp && fp[0] == '1';  // measured: no gain (profiles/sweep_r2.txt), so off unless asked for
+    const int medium = split ? (least + greatest) / 2 : least;
+    for (auto &st : ps->b) CUDA_TRY(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, medium));
+    if (split)
+        for (auto &st : ps->m) CUDA_TRY(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, least));
     for (auto &e : ps->ev_in) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto &e : ps->ev_fit) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     *out = ps;
     return MDB_OK;
+}
+
+static void release_pipe_stream_pool(int dev)  // destroys the idle stream sets of one device
+{
+    std::vector<PipeStreams *> mine;
+    {
+        std::lock_guard<std::mutex> lock(g_pipe_mutex);
+        auto range = g_pipe_pool.equal_range(dev);
+        for (auto it = range.first; it != range.second; ++it) mine.push_back(it->second);
+        g_pipe_pool.erase(range.first, range.second);
+    }
+    for (PipeStreams *ps : mine) {
+        if (ps->copy) cudaStreamDestroy(ps->copy);
+        for (auto st : ps->a) if (st) cudaStreamDestroy(st);
+        for (auto st : ps->b) if (st) cudaStreamDestroy(st);
+        for (auto st : ps->m) if (st) cudaStreamDestroy(st);
+        for (auto e : ps->ev_in) if (e) cudaEventDestroy(e);
+        for (auto e : ps->ev_fit) if (e) cudaEventDestroy(e);
+        delete ps;
+    }
 }
 
 static void release_pipe_streams(PipeStreams *ps)
@@ -1626,6 +1681,7 @@ static mdb_status run_pipeline(const mdb_deconvoluter &dc, const std::vector<Hos
             cudaStreamSynchronize(pipe->copy);
             for (size_t i = 0; i < n_a; ++i) cudaStreamSynchronize(pipe->a[i]);
             for (size_t i = 0; i < depth; ++i) cudaStreamSynchronize(pipe->b[i]);
+            for (size_t i = 0; i < depth; ++i) if (pipe->m[i]) cudaStreamSynchronize(pipe->m[i]);
             release_pipe_streams(pipe);
             pipe = nullptr;
         }
@@ -1654,7 +1710,9 @@ static mdb_status run_pipeline(const mdb_deconvoluter &dc, const std::vector<Hos
         ck.s_copy = pipe->copy;
         ck.s_a = pipe->a[k % n_a];
         ck.s_b = pipe->b[k % depth];
+        ck.s_m = pipe->m[k % depth];  // null when MDB_FIT_PRIORITY=0
         ck.ev_in = pipe->ev_in[k % ring];
+        ck.ev_fit = pipe->ev_fit[k % ring];
         ck.first = next_first;
         size_t count = std::min(csz, n_spectra - next_first);
         if (n_spectra - next_first - count < csz / 4) count = n_spectra - next_first;  // no tiny straggler chunk

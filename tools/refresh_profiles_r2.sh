@@ -10,7 +10,7 @@ $B5 > gpurun_out/p5.json 2> gpurun_out/p5.err || { tail -5 gpurun_out/p5.err; ex
 ncu --metrics gpu__time_duration.sum --clock-control none -s 300 -c 400 --csv --log-file gpurun_out/launches_r2.csv $B5 > gpurun_out/ncu_launches_r2.log 2>&1
 full() {  # name, kernel regex, skip, command...
   local name=$1 regex=$2 skip=$3; shift 3
-  ncu --set full --clock-control none --import-source on -k regex:$regex -s $skip -c 1 -o gpurun_out/prof_${name}_r2 -f "$@" > gpurun_out/ncu_${name}_r2.log 2>&1
+  ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:$regex -s $skip -c 1 -o gpurun_out/prof_${name}_r2 -f "$@" > gpurun_out/ncu_${name}_r2.log 2>&1
   tail -1 gpurun_out/ncu_${name}_r2.log
 }
 full fit_iter fit_iter_kernel 25 $B5

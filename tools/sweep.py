@@ -66,8 +66,9 @@ def main():
         assert lib.mdb_deconvoluter_set_superposition_mode(dec, sup) == 0
         for kk, v in env.items():
             os.environ[kk] = v
-        if "MDB_STREAM_PRIORITIES" in env:
-            lib.mdb_release_workspaces()  # streams are created with the workspaces
+        recreate = any(k in env for k in ("MDB_STREAM_PRIORITIES", "MDB_FIT_PRIORITY"))
+        if recreate:
+            lib.mdb_release_workspaces()  # streams are created with the pooled stream sets
         step()
         ts = []
         for _ in range(args.steps):
@@ -80,7 +81,7 @@ def main():
             ts.append(e0.elapsed_time(e1))
         for kk in env:
             del os.environ[kk]
-        if "MDB_STREAM_PRIORITIES" in env:
+        if recreate:
             lib.mdb_release_workspaces()
         print(f"{args.workload} {S} spectra | {setting or 'default':40s} | {S / (np.median(ts) / 1e3):9.0f} spectra/s | ms {[round(t, 1) for t in ts]}", flush=True)
 
