@@ -59,7 +59,8 @@ WORKLOADS = {
 FP64_LANES_PER_SM, N_SM = 64, 148
 FP64_INSTR_PER_EVAL = 12  # counted from SASS: sub, mul, add, 8 for the IEEE division, accumulate
 SUP_MODES = {"exact": 0, "fast": 1}  # include/mdb200.h MDB_SUPERPOSITION_*
-FP64_INSTR_PER_EVAL_FAST = 6  # MDB_SUPERPOSITION_FAST (K7 / K8 only): sub, fma, 3 fma for the reciprocal, fma accumulate
+FP64_INSTR_PER_EVAL_FAST = 5.25  # MDB_SUPERPOSITION_FAST (K7 / K8 only), four Lorentzians behind one reciprocal (lorentz_quad_ulp):
+# 4 sub, 4 fma, 3 + 6 mul / fma for the common denominator and numerator, 3 fma for the reciprocal, 1 fma accumulate = 21 per 4 (SASS)
 FLOPS_PER_EVAL = 5        # algorithmic: sub, mul, add, div, accumulate
 
 

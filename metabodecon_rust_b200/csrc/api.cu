@@ -745,6 +745,7 @@ static void precompute_spec(HostSpec &h, const mdb_deconvoluter &dc)
 // pipeline (the job is submitted when the chunk is created, one iteration before its stage A), in
 // parts of ~32 MB so that the DMA of part p runs while part p+1 is still being gathered.
 // ---------------------------------------------------------------------------------------------
+extern "C" __attribute__((visibility("hidden"))) void mdb_host_row_copy(double *dst, const double *src, size_t n);  // hostcopy.cpp
 struct HostSpec;
 struct StageJob {
     std::vector<const double *> src;     // row pointers
@@ -801,7 +802,7 @@ class Stager {
             for (;;) {
                 const size_t r = j->next.fetch_add(1);
                 if (r >= rows) break;
-                std::memcpy(j->dst + j->off[r], j->src[r], j->len[r] * 8);
+                mdb_host_row_copy(j->dst + j->off[r], j->src[r], j->len[r]);  // non-temporal stores (hostcopy.cpp)
                 if (j->part_left[j->part_of_row[r]].fetch_sub(1) == 1) {
                     std::lock_guard<std::mutex> lk(j->m);
                     j->cv.notify_all();
@@ -871,6 +872,13 @@ static const DeviceInfo &device_info()
     return di;
 }
 static int smem_optin_limit() { return device_info().smem_optin; }
+// MDB_SUPERPOSITION_FAST: four Lorentzians per reciprocal (lorentz_quad_ulp) unless MDB_SUP_GROUP=1 asks for
+// the one-at-a-time few-ulp form (measurement aid; read at every launch so that a sweep can flip it)
+static bool sup_quad()
+{
+    const char *env = std::getenv("MDB_SUP_GROUP");
+    return !(env && env[0] == '1');
+}
 constexpr int FIT_WARP_CTA_MAX = 1024;  // K6: spectra with at most this many selected peaks run one-warp CTAs
 static int sm_count() { return device_info().sms; }
 
@@ -1398,7 +1406,8 @@ static mdb_status stage_b(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
         dim3 grid((unsigned)((ck.max_seg_len + per_block - 1) / per_block), (unsigned)n_seg);
         if (grid.x > 0) {
             prof_begin(&ck.spans, MDB_KERNEL_MSE_SUPERPOSITION, sm);
-            auto kern = ulp ? (r == 16 ? superposition_kernel<2, 16, 2> : r == 8 ? superposition_kernel<2, 8, 2> : superposition_kernel<2, 2, 2>)
+            auto kern = ulp ? (sup_quad() ? (r == 16 ? superposition_kernel<2, 16, 4> : r == 8 ? superposition_kernel<2, 8, 4> : superposition_kernel<2, 2, 4>)
+                                          : (r == 16 ? superposition_kernel<2, 16, 2> : r == 8 ? superposition_kernel<2, 8, 2> : superposition_kernel<2, 2, 2>))
                             : (r == 8 ? superposition_kernel<1, 8, 1> : superposition_kernel<1, 2, 1>);
             kern<<<grid, SUP_THREADS, LOR_SMEM_BYTES, sm>>>(nullptr, 0, nullptr, 0, ws.resid.as<double>(), d_desc, d_fd,
                                                                   ws.segs.as<Segment>(), ws.lor.as<double>(),
@@ -2256,7 +2265,8 @@ static int superposition_points_per_thread(size_t n, bool ulp)
 }
 static SupKernel superposition_kernel_for(int r, bool ulp)
 {
-    return ulp ? (r == 16 ? superposition_kernel<0, 16, 2> : r == 8 ? superposition_kernel<0, 8, 2> : superposition_kernel<0, 2, 2>)
+    return ulp ? (sup_quad() ? (r == 16 ? superposition_kernel<0, 16, 4> : r == 8 ? superposition_kernel<0, 8, 4> : superposition_kernel<0, 2, 4>)
+                             : (r == 16 ? superposition_kernel<0, 16, 2> : r == 8 ? superposition_kernel<0, 8, 2> : superposition_kernel<0, 2, 2>))
                : (r == 8 ? superposition_kernel<0, 8, 1> : superposition_kernel<0, 2, 1>);
 }
 

@@ -1,8 +1,8 @@
 """The library's DEFAULT arithmetic for the two superposition kernels that do not feed back into
 the fit -- K7 (the full-grid superposition behind Deconvolution.mse, deconvoluter.rs:540-543,
 828-862) and K8 (Lorentzian::superposition_vec / par_superposition_vec, lorentzian.rs:631-663):
-MDB_SUPERPOSITION_FAST, 6 instead of 12 FP64 instructions per evaluation (kernels.cuh,
-lorentz_step_ulp).
+MDB_SUPERPOSITION_FAST, 5.25 instead of 12 FP64 instructions per evaluation (kernels.cuh,
+lorentz_quad_ulp: four Lorentzians behind one reciprocal; lorentz_step_ulp for what is left over).
 
 Bar (BASELINE.json north_star): peak sets bit-exact; Lorentzian parameters and superposition values
 within 1e-9 relative.  What is asserted here, against the CPU oracle on the same inputs:
@@ -100,6 +100,41 @@ def test_wide_dynamic_range_inside_the_fast_domain():
     fin = np.isfinite(want)
     assert fin.any() and np.array_equal(np.isfinite(got), fin)
     assert rel_err(got[fin], want[fin]) <= TOL_VALUES
+
+
+def test_four_lorentzians_per_reciprocal_domain_edges_and_remainders(monkeypatch):
+    # lorentz_quad_ulp (kernels.cuh): N / P over groups of four inside |sfhw|, hw2 in [2^-200, 2^200],
+    # |maxp|, |x| <= 2^100; parameter counts that leave 1, 2 and 3 Lorentzians for the one-at-a-time tail
+    rng = np.random.default_rng(14)
+    for p in (4, 5, 6, 7, 512 + 2, 1024 + 3):
+        lor = np.stack([np.exp2(rng.uniform(-195, 195, p)), np.exp2(rng.uniform(-195, 195, p)),
+                        rng.uniform(-5, 5, p) * np.exp2(rng.uniform(-60, 95, p))], axis=1)
+        x = rng.uniform(-5, 5, 2000) * np.exp2(rng.uniform(-60, 95, 2000))
+        want = O.superposition_vec(x, lor)
+        got = superposition_vec_array(x, lor)
+        assert np.isfinite(want).all() and np.isfinite(got).all()
+        assert rel_err(got, want) <= TOL_VALUES, f"p={p}: {rel_err(got, want):.3e}"
+    # one parameter just outside the quad domain (hw2 = 2^-210): that tile runs one at a time, still in tolerance
+    lor = random_lorentzians(rng, 600)
+    lor[17, 1] = 2.0 ** -210
+    x = np.linspace(-2.2, 11.8, 5000)
+    assert rel_err(superposition_vec_array(x, lor), O.superposition_vec(x, lor)) <= TOL_VALUES
+    # mixed signs: a group's error is bounded relative to the sum of the magnitudes of its terms
+    lor = random_lorentzians(rng, 801)
+    lor[::3, 0] *= -1.0
+    want = O.superposition_vec(x, lor)
+    mag = O.superposition_vec(x, np.abs(lor))
+    got = superposition_vec_array(x, lor)
+    assert float(np.max(np.abs(got - want) / mag)) <= TOL_VALUES
+    # the one-at-a-time few-ulp form (MDB_SUP_GROUP=1, measurement aid) agrees to the same tolerance
+    lor = random_lorentzians(rng, 2143)
+    want = O.superposition_vec(x, lor)
+    quad = superposition_vec_array(x, lor)
+    monkeypatch.setenv("MDB_SUP_GROUP", "1")
+    single = superposition_vec_array(x, lor)
+    monkeypatch.delenv("MDB_SUP_GROUP")
+    assert rel_err(quad, want) <= TOL_VALUES and rel_err(single, want) <= TOL_VALUES
+    assert not np.array_equal(quad, single) or True  # different roundings are expected, not required
 
 
 def test_out_of_domain_operands_take_the_ieee_loop_bit_exactly():
