@@ -874,6 +874,13 @@ static const DeviceInfo &device_info()
 static int smem_optin_limit() { return device_info().smem_optin; }
 // MDB_SUPERPOSITION_FAST: four Lorentzians per reciprocal (lorentz_quad_ulp) unless MDB_SUP_GROUP=1 asks for
 // the one-at-a-time few-ulp form (measurement aid; read at every launch so that a sweep can flip it)
+// MDB_STREAM_GENERIC=1 (tests): the latency forms of K1 (smooth_stream.cuh, small_fused.cuh) run their any-window
+// interior loop even for the windows they have a specialised loop for
+static bool stream_generic_env()
+{
+    const char *env = std::getenv("MDB_STREAM_GENERIC");
+    return env && env[0] == '1';
+}
 static bool sup_quad()
 {
     const char *env = std::getenv("MDB_SUP_GROUP");
@@ -908,8 +915,11 @@ static mdb_status launch_smooth(cudaStream_t stream, const SpecDesc *d_desc, con
     prof_begin(spans, MDB_KERNEL_SMOOTH, stream);
     if (streamable) {
         const size_t smem = smooth_stream_smem_bytes(iters);
-        CUDA_TRY(cudaFuncSetAttribute(smooth_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smooth_stream_kernel<<<(unsigned)S, STREAM_THREADS, smem, stream>>>(d_desc, iters, window);
+        // interior loop specialised for the default window and the ones optimize_settings tries (smooth_stream.cuh)
+        auto kern = window == 5 ? smooth_stream_kernel<5> : window == 3 ? smooth_stream_kernel<3> : window == 7 ? smooth_stream_kernel<7> : smooth_stream_kernel<0>;
+        if (stream_generic_env()) kern = smooth_stream_kernel<0>;  // tests: the any-window form
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)S, STREAM_THREADS, smem, stream>>>(d_desc, iters, window);
         LAUNCH_CHECK();
     } else if (fn && aligned && !(force && force[0] == '1')) {
         const int groups = 32 / iters;  // spectra per warp: one lane per (spectrum, pass)
@@ -1969,7 +1979,7 @@ static mdb_status run_small(const mdb_deconvoluter &dc, const std::vector<HostSp
         small_fused_kernel<<<(unsigned)S, SMALL_THREADS, smem, ws.stream>>>(
             d_desc, reinterpret_cast<const SmallDesc *>(db + off_small), n_al, dc.selection.kind,
             smooth_fused ? (int)dc.smoothing.iterations : 0, (int)dc.smoothing.window_size,
-            dc.sup_mode == MDB_SUPERPOSITION_FAST ? 1 : 0, d_stamps);
+            (dc.sup_mode == MDB_SUPERPOSITION_FAST ? 1 : 0) | (stream_generic_env() ? 2 : 0), d_stamps);
         LAUNCH_CHECK();
         prof_end(&spans, ws.stream, (double)S);
         CUDA_TRY(cudaStreamSynchronize(ws.stream));

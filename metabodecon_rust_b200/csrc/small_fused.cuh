@@ -206,12 +206,20 @@ __device__ __forceinline__ void small_mse_block(const double *__restrict__ x, co
 constexpr int SMALL_SMOOTH_U = 8;
 constexpr int SMALL_SMOOTH_MAX_ITERS = 32;
 
-__device__ __forceinline__ void small_smooth_warp(double *rows, int row_stride, int n, int iters, int w, double *sink)
+// WS: the window size when the interior loop is specialised for it (3, 5, 7), 0 = any window (runtime w_arg).
+// The specialised loop keeps the aligned 8-point blocks m-1, m, m+1 of the lane's input row in registers
+// (incoming and outgoing values of every step are register operands chosen at compile time; four 16-byte
+// loads per round instead of sixteen 8-byte ones), fetches block m+2 two rounds early and stores the
+// outputs of block m-1 one round late, so that nothing issued in a round depends on that round's chain;
+// that costs two more blocks of distance between consecutive passes (see smooth_stream.cuh).
+template <int WS>
+__device__ __forceinline__ void small_smooth_warp(double *rows, int row_stride, int n, int iters, int w_arg, double *sink)
 {
     constexpr int U = SMALL_SMOOTH_U;
     const int lane = threadIdx.x & 31;
+    const int w = WS > 0 ? WS : w_arg;
     const int r = w / 2;
-    const int db = 2 + (max(r, w - r) + U - 1) / U;
+    const int db = WS > 0 ? 4 : 2 + (max(r, w - r) + U - 1) / U;
     const int n_blocks = (n + U - 1) / U;
     // pass p reads row p&1 and writes the other one
     const int in_o = (lane & 1) * row_stride, out_o = row_stride - in_o;
@@ -314,6 +322,70 @@ __device__ __forceinline__ void small_smooth_warp(double *rows, int row_stride, 
     const int f0 = (w - r + U - 1) / U, f1 = (n - r) / U - 1;
     const int b_lo = f0 + (iters - 1) * db, b_hi = f1;  // rounds in which EVERY pass is on an interior block
     int b = 0;
+    if constexpr (WS > 0) {
+    if (b_hi - b_lo >= 8) {
+        for (; b < b_lo; ++b) edge_round(b);
+        constexpr int RR = WS / 2, QB = WS - RR;          // x[i + RR] comes in, x[i - QB] goes out
+        static_assert(RR <= U && QB <= U, "window wider than two blocks");
+        double B0[U], B1[U], B2[U], B3[U];                // aligned blocks m-1, m, m+1, m+2 of the input row (rotating)
+        double prA[U], prB[U];                            // outputs of block m-1, not yet stored: in prB between rounds
+        int m = b + blk0;                                 // this lane's block in the coming round
+        const int last_blk = row_stride / U - 1;          // rows are a multiple of U long; the prefetch never leaves the row
+        const uint32_t sink_s = smem_addr(sink);
+        uint32_t po_prev = 0;
+        uint32_t po_s2 = ghost ? sink_s : out_s + 8u * (uint32_t)(m * U);
+        const uint32_t po_step2 = ghost ? 0u : 8u * U;
+        asm volatile("" : "+r"(po_s2));
+        auto load_aligned = [&](double (&x)[U], int blk) {
+            const uint32_t pa = in_s + 8u * (uint32_t)(min(blk, last_blk) * U);
+#pragma unroll
+            for (int u = 0; u < U; u += 2) asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x[u]), "=d"(x[u + 1]) : "r"(pa + 8u * u) : "memory");
+        };
+        auto store_pending = [&](const double (&ps)[U]) {
+#pragma unroll
+            for (int u = 0; u < U; u += 2) asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(po_prev + 8u * u), "d"(ps[u]), "d"(ps[u + 1]) : "memory");
+        };
+        auto lean_round = [&](const double (&pm)[U], const double (&p0)[U], const double (&p1)[U], double (&ld)[U],
+                              double (&pw)[U], const double (&ps)[U], const bool pend) {
+            load_aligned(ld, m + 2);
+            if (pend) store_pending(ps);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const double a = (u + RR < U) ? p0[(u + RR) % U] : p1[(u + RR) % U];
+                const double q = (u >= QB) ? p0[(u + U - QB) % U] : pm[(u + U - QB) % U];
+                sum = __dadd_rn(sum, a);
+                sum = __dsub_rn(sum, q);
+                pw[u] = __dmul_rn(sum, div);
+            }
+            po_prev = po_s2;
+            po_s2 += po_step2;
+            ++m;
+            __syncwarp();
+        };
+        load_aligned(B0, m - 1);
+        load_aligned(B1, m);
+        load_aligned(B2, m + 1);
+        int left = b_hi - b + 1;  // interior rounds to go
+        b = b_hi + 1;
+        lean_round(B0, B1, B2, B3, prA, prB, false);  // first lean round: nothing to store yet
+#pragma unroll
+        for (int u = 0; u < U; ++u) { B0[u] = B1[u]; B1[u] = B2[u]; B2[u] = B3[u]; prB[u] = prA[u]; }
+        --left;
+        for (; left >= 4; left -= 4) {
+            lean_round(B0, B1, B2, B3, prA, prB, true);
+            lean_round(B1, B2, B3, B0, prB, prA, true);
+            lean_round(B2, B3, B0, B1, prA, prB, true);
+            lean_round(B3, B0, B1, B2, prB, prA, true);
+        }
+        for (; left >= 1; --left) {
+            lean_round(B0, B1, B2, B3, prA, prB, true);
+#pragma unroll
+            for (int u = 0; u < U; ++u) { B0[u] = B1[u]; B1[u] = B2[u]; B2[u] = B3[u]; prB[u] = prA[u]; }
+        }
+        store_pending(prB);
+        __syncwarp();
+    }
+    } else {
     if (b_hi - b_lo >= 3) {
         for (; b < b_lo; ++b) edge_round(b);
         double a0[U], q0[U], a1[U], q1[U];
@@ -333,13 +405,16 @@ __device__ __forceinline__ void small_smooth_warp(double *rows, int row_stride, 
         }
         if (left == 1) lean_round(a0, q0, a1, q1, false);
     }
+    }
     for (; b < rounds; ++b) edge_round(b);
 }
 
 __global__ void __launch_bounds__(SMALL_THREADS)
 small_fused_kernel(const SpecDesc *__restrict__ sd, const SmallDesc *__restrict__ xd, int n_al, int selector_kind,
-                   int smooth_iters, int smooth_window, int fast_mse, long long *__restrict__ stamps)
+                   int smooth_iters, int smooth_window, int flags, long long *__restrict__ stamps)
 {
+    const int fast_mse = flags & 1;        // MDB_SUPERPOSITION_FAST tail
+    const int generic_smooth = flags & 2;  // MDB_STREAM_GENERIC=1 (tests): the any-window smoothing loop
     // optional phase clock of CTA 0 (MDB_SMALL_STAMPS=1, development aid): SM cycles at phase ends
     int stamp_k = 0;
     auto stamp = [&]() { if (stamps && blockIdx.x == 0 && threadIdx.x == 0) stamps[stamp_k++] = clock64(); };
@@ -387,7 +462,12 @@ small_fused_kernel(const SpecDesc *__restrict__ sd, const SmallDesc *__restrict_
         const double *__restrict__ y = d.y;
         for (int j = t; j < n; j += SMALL_THREADS) row0[j] = y[j];
         __syncthreads();
-        if (t < 32) small_smooth_warp(row0, n_al, n, smooth_iters, smooth_window, smooth_sink);
+        if (t < 32) {
+            if (smooth_window == 5 && generic_smooth == 0) small_smooth_warp<5>(row0, n_al, n, smooth_iters, 5, smooth_sink);
+            else if (smooth_window == 3 && generic_smooth == 0) small_smooth_warp<3>(row0, n_al, n, smooth_iters, 3, smooth_sink);
+            else if (smooth_window == 7 && generic_smooth == 0) small_smooth_warp<7>(row0, n_al, n, smooth_iters, 7, smooth_sink);
+            else small_smooth_warp<0>(row0, n_al, n, smooth_iters, smooth_window, smooth_sink);
+        }
         __syncthreads();
         ys = (smooth_iters & 1) ? row1 : row0;
     }

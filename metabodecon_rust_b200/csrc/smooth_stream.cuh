@@ -28,7 +28,7 @@ constexpr int STREAM_THREADS = 128;   // warp 0: chain; warps 1-3: movers
 constexpr int STREAM_MOVERS = STREAM_THREADS - 32;
 constexpr int STREAM_R = 2048;        // ring length in points (power of two)
 constexpr int STREAM_U = 8;           // points per round
-constexpr int STREAM_G = 32;          // rounds between flow-control checks
+constexpr int STREAM_G = 64;          // rounds between flow-control checks
 constexpr int STREAM_MAX_ITERS = 12;  // (passes + 1) rings of 16 KB must fit into shared memory
 
 __host__ __device__ inline size_t smooth_stream_smem_bytes(int iters) { return (size_t)(iters + 1) * (STREAM_R + 8) * 8; }
@@ -51,8 +51,20 @@ __device__ __forceinline__ void st_volatile_s32(int *p, int v)
     asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(smem_addr(p)), "r"(v) : "memory");
 }
 
+__device__ __forceinline__ void lds_f64x2(uint32_t a, double &v0, double &v1)
+{
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v0), "=d"(v1) : "r"(a) : "memory");
+}
+__device__ __forceinline__ void sts_f64x2(uint32_t a, double v0, double v1)
+{
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(v0), "d"(v1) : "memory");
+}
+
+// WS: the window size when it is one the interior loop is specialised for (3, 5, 7: the default and the
+// values optimize_settings tries), 0 = any window (runtime `w`, sixteen 8-byte loads per round).
+template <int WS>
 __global__ void __launch_bounds__(STREAM_THREADS)
-smooth_stream_kernel(const SpecDesc *__restrict__ sd, int iters, int w)
+smooth_stream_kernel(const SpecDesc *__restrict__ sd, int iters, int w_arg)
 {
     extern __shared__ __align__(16) unsigned char stream_smem[];
     __shared__ StreamFlow flow;
@@ -61,8 +73,14 @@ smooth_stream_kernel(const SpecDesc *__restrict__ sd, int iters, int w)
     const SpecDesc d = sd[blockIdx.x];
     const int n = d.n;
     const int t = threadIdx.x, lane = t & 31;
+    const int w = WS > 0 ? WS : w_arg;
     const int r = w / 2;
-    const int db = 2 + (max(r, w - r) + U - 1) / U;   // blocks between consecutive passes
+    // blocks between consecutive passes.  Any-window loop: the consumer's reach into the producer's stream
+    // (ceil(max(r, w - r) / U) blocks), one round until a store is visible (__syncwarp), one of slack.
+    // Specialised loop: it fetches ALIGNED block m+2 in round m (no reach beyond the block), the producer stores
+    // a block one round after computing it and the store is visible one round later: m + 2 computed in round
+    // m + 2 - db of the consumer's clock, stored in m + 3 - db, readable from m + 4 - db <= m.
+    const int db = WS > 0 ? 4 : 2 + (max(r, w - r) + U - 1) / U;
     const int n_blocks = (n + U - 1) / U;
     const int rounds = n_blocks + (iters - 1) * db;
     double *rings = reinterpret_cast<double *>(stream_smem);
@@ -88,12 +106,23 @@ smooth_stream_kernel(const SpecDesc *__restrict__ sd, int iters, int w)
             // feed: lane 0 of the chain is at block `taken`, its lowest live index is taken*U + r - w
             const int feed_limit = min(n, taken * U + r - w + R - U);
             if (fed < feed_limit) {
+                // all eight loads of a thread in flight at once: a mover pass costs one global-memory round trip,
+                // not eight (the movers, not the chain, bounded the kernel once the chain loop had been tightened)
                 const int hi = min(feed_limit, fed + 8 * STREAM_MOVERS);
-                for (int i = fed + m; i < hi; i += STREAM_MOVERS) {
-                    const double v = y[i];
-                    const int s = i & (R - 1);
-                    ring_in[s] = v;
-                    if (s < 8) ring_in[R + s] = v;
+                double v[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int i = fed + m + k * STREAM_MOVERS;
+                    v[k] = (i < hi) ? __ldg(y + i) : 0.0;
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int i = fed + m + k * STREAM_MOVERS;
+                    if (i < hi) {
+                        const int s = i & (R - 1);
+                        ring_in[s] = v[k];
+                        if (s < 8) ring_in[R + s] = v[k];
+                    }
                 }
                 fed = hi;
                 worked = true;
@@ -102,7 +131,11 @@ smooth_stream_kernel(const SpecDesc *__restrict__ sd, int iters, int w)
             const int done_pts = (taken >= rounds) ? n : min(n, max(0, taken - (iters - 1) * db) * U);
             if (drained < done_pts) {
                 const int hi = min(done_pts, drained + 8 * STREAM_MOVERS);
-                for (int i = drained + m; i < hi; i += STREAM_MOVERS) ys[i] = ring_out[i & (R - 1)];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int i = drained + m + k * STREAM_MOVERS;
+                    if (i < hi) ys[i] = ring_out[i & (R - 1)];
+                }
                 drained = hi;
                 worked = true;
             }
@@ -120,10 +153,15 @@ smooth_stream_kernel(const SpecDesc *__restrict__ sd, int iters, int w)
 
     // -------------------------------------------------------------------- chain warp
     // Lanes without a pass shadow lane 0 (same reads, stores to a sink): the warp stays converged.
-    const bool ghost = lane >= iters;
+    int ghost_i = lane >= iters ? 1 : 0;
+    asm volatile("mov.b32 %0, %0;" : "+r"(ghost_i));  // opaque, see below
+    const bool ghost = ghost_i != 0;
     const int pl = ghost ? 0 : lane;
-    const uint32_t in_s = smem_addr(rings + (size_t)pl * RS), out_s = ghost ? smem_addr(sink) : smem_addr(rings + (size_t)(pl + 1) * RS);
-    const uint32_t out_mask = ghost ? 0u : (uint32_t)(R - 1);   // ghosts: every store lands in the sink
+    uint32_t in_s = smem_addr(rings + (size_t)pl * RS), out_s = ghost ? smem_addr(sink) : smem_addr(rings + (size_t)(pl + 1) * RS);
+    uint32_t out_mask = ghost ? 0u : (uint32_t)(R - 1);   // ghosts: every store lands in the sink
+    // opaque to ptxas from here on: it otherwise re-derives these inside the chain loop (S2R SR_TID / SR_CgaCtaId
+    // and the address arithmetic behind them, with the in-order warp waiting for the special-register reads)
+    asm volatile("mov.b32 %0, %0;\n\tmov.b32 %1, %1;\n\tmov.b32 %2, %2;" : "+r"(in_s), "+r"(out_s), "+r"(out_mask));
     int blk0 = ghost ? 0 : -lane * db;                          // this lane's block in round b is b + blk0
     double sum = 0.0, div = 1.0;
 
@@ -189,6 +227,95 @@ smooth_stream_kernel(const SpecDesc *__restrict__ sd, int iters, int w)
         }
         b = first;
     }
+    if constexpr (WS > 0) {
+    if (b_hi - b_lo >= 8 && b == b_lo) {
+        // Window size known at compile time (WS = w): the chain warp keeps the ALIGNED 8-point blocks
+        // m-1, m, m+1 of its input stream in registers, so the incoming value x[i + r] and the outgoing
+        // x[i + r - w] of every step are register operands picked at compile time, and a round costs
+        // four 16-byte shared loads (block m+2) instead of sixteen 8-byte ones.  Software pipeline over
+        // rounds: in round k the warp (1) fetches block k+2, (2) stores the outputs of block k-1, which
+        // have been sitting in registers since the last round, (3) runs the chain over block k.  Nothing
+        // issued in a round depends on that round's chain, so the in-order warp never waits for a
+        // product or a load before it may start the next chain.  The store delay and the deeper
+        // prefetch are what the larger pass distance `db` pays for.
+        constexpr int RR = WS / 2, QB = WS - RR;          // x[i + RR] comes in, x[i - QB] goes out
+        static_assert(RR <= U && QB <= U, "window wider than two blocks");
+        double B0[U], B1[U], B2[U], B3[U];                // aligned blocks m-1, m, m+1, m+2 (rotating)
+        // outputs of block m-1, not yet stored: always in prB between rounds.  Two sets, so that the products of
+        // a round never overwrite registers a store issued in the same round has yet to read
+        double prA[U], prB[U];
+        int m = b + blk0;                                 // this lane's block in the coming round
+        uint32_t so = ((uint32_t)(m * U)) & out_mask;     // output slot of block m
+        uint32_t so_prev = 0;
+        auto load_aligned = [&](double (&x)[U], int blk) {
+            const uint32_t pa = in_s + 8u * ((uint32_t)(blk * U) & (uint32_t)(R - 1));
+#pragma unroll
+            for (int u = 0; u < U; u += 2) lds_f64x2(pa + 8u * u, x[u], x[u + 1]);
+        };
+        auto store_pending = [&](const double (&ps)[U]) {
+            const uint32_t po = out_s + 8u * so_prev;
+#pragma unroll
+            for (int u = 0; u < U; u += 2) sts_f64x2(po + 8u * u, ps[u], ps[u + 1]);
+            if (so_prev == 0 && !ghost) {                 // the mirror of slots [0, 8) (read by the edge rounds)
+#pragma unroll
+                for (int u = 0; u < U; u += 2) sts_f64x2(out_s + 8u * (R + u), ps[u], ps[u + 1]);
+            }
+        };
+        // one round: chain over block m (inputs from pm / p0 / p1 = blocks m-1 / m / m+1), products into pw;
+        // block m+2 fetched into ld; the products of the round before (ps) stored
+        auto lean_round = [&](const double (&pm)[U], const double (&p0)[U], const double (&p1)[U], double (&ld)[U],
+                              double (&pw)[U], const double (&ps)[U], const bool pend) {
+            load_aligned(ld, m + 2);
+            if (pend) store_pending(ps);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const double a = (u + RR < U) ? p0[(u + RR) % U] : p1[(u + RR) % U];
+                const double q = (u >= QB) ? p0[(u + U - QB) % U] : pm[(u + U - QB) % U];
+                sum = __dadd_rn(sum, a);
+                sum = __dsub_rn(sum, q);
+                pw[u] = __dmul_rn(sum, div);
+            }
+            so_prev = so;
+            ++m;
+            so = (so + U) & out_mask;
+            __syncwarp();
+        };
+        flow_wait(min(b_hi + 1, b + G));
+        load_aligned(B0, m - 1);
+        load_aligned(B1, m);
+        load_aligned(B2, m + 1);
+        bool pend = false;
+        while (b <= b_hi) {
+            const int e = min(b_hi + 1, b + G);      // this group: rounds [b, e)
+            // the prefetch of the group's last round reaches two blocks into the next group
+            flow_wait(min(b_hi + 1, e + 2));
+            int left = e - b;
+            if (!pend && left >= 1) {                // first lean round of all: nothing to store yet
+                lean_round(B0, B1, B2, B3, prA, prB, false);
+#pragma unroll
+                for (int u = 0; u < U; ++u) { B0[u] = B1[u]; B1[u] = B2[u]; B2[u] = B3[u]; prB[u] = prA[u]; }
+                pend = true;
+                --left;
+            }
+            for (; left >= 4; left -= 4) {
+                lean_round(B0, B1, B2, B3, prA, prB, true);
+                lean_round(B1, B2, B3, B0, prB, prA, true);
+                lean_round(B2, B3, B0, B1, prA, prB, true);
+                lean_round(B3, B0, B1, B2, prB, prA, true);
+            }
+            for (; left >= 1; --left) {
+                lean_round(B0, B1, B2, B3, prA, prB, true);
+#pragma unroll
+                for (int u = 0; u < U; ++u) { B0[u] = B1[u]; B1[u] = B2[u]; B2[u] = B3[u]; prB[u] = prA[u]; }
+            }
+            b = e;
+            // block b-1 of every pass is still in registers: the movers are told about one round less
+            if (b <= b_hi) publish(b - 1);
+        }
+        if (pend) { store_pending(prB); }
+        publish(b);
+    }
+    } else {
     if (b_hi - b_lo >= 3 && b == b_lo) {
         double a0[U], q0[U], a1[U], q1[U];
         const uint32_t w8 = 8u * (uint32_t)w;
@@ -245,6 +372,7 @@ smooth_stream_kernel(const SpecDesc *__restrict__ sd, int iters, int w)
             b = e;
             publish(b);
         }
+    }
     }
     for (; b < rounds; b += G) {
         const int e = min(rounds, b + G);

@@ -270,10 +270,16 @@ def test_smoothing_stream_kernel_ring_edges(n, monkeypatch):
     rng = np.random.default_rng(n)
     y = rng.normal(0, 1e4, n)
     yi = np.rint(y)
-    for it, w in [(3, 3), (1, 2), (2, 2), (12, 3), (5, 8), (4, 9), (2, 33), (3, 64), (1, 7)]:
+    # windows 3, 5 and 7 take the interior loop specialised on the window (register-resident blocks, stores
+    # one round late); MDB_STREAM_GENERIC=1 sends them through the any-window loop as well
+    for it, w in [(3, 3), (1, 2), (2, 2), (12, 3), (5, 8), (4, 9), (2, 33), (3, 64), (1, 7), (2, 5), (12, 5), (7, 7), (1, 5)]:
         want = O.smooth_values(y, it, w)
         assert_bit_equal(gpu_smooth(y, it, w), want, f"stream n={n} ({it},{w})")
         assert_bit_equal(gpu_smooth(yi, it, w), O.smooth_values(yi, it, w), f"stream n={n} ({it},{w}) integer")
+        if w in (3, 5, 7):
+            monkeypatch.setenv("MDB_STREAM_GENERIC", "1")
+            assert_bit_equal(gpu_smooth(y, it, w), want, f"stream, any-window loop n={n} ({it},{w})")
+            monkeypatch.delenv("MDB_STREAM_GENERIC")
         monkeypatch.setenv("MDB_SMOOTH_STREAM", "0")
         assert_bit_equal(gpu_smooth(y, it, w), want, f"lanes n={n} ({it},{w})")
         monkeypatch.delenv("MDB_SMOOTH_STREAM")
@@ -977,6 +983,15 @@ def test_small_path_is_one_launch_and_matches_general_path_and_oracle(monkeypatc
          O.Settings(smoothing_iterations=1, smoothing_window=40, threshold=1.5)),
         (lambda d: (d.set_moving_average_smoother(33, 3), d.set_noise_score_selector(1.5)),  # > 32 passes: smoothing launched separately
          O.Settings(smoothing_iterations=33, smoothing_window=3, threshold=1.5)),
+        # windows 3, 5, 7: the interior loop specialised on the window (register-resident blocks), many passes
+        (lambda d: (d.set_moving_average_smoother(12, 3), d.set_noise_score_selector(1.5)),
+         O.Settings(smoothing_iterations=12, smoothing_window=3, threshold=1.5)),
+        (lambda d: (d.set_moving_average_smoother(9, 7), d.set_noise_score_selector(1.5)),
+         O.Settings(smoothing_iterations=9, smoothing_window=7, threshold=1.5)),
+        (lambda d: (d.set_moving_average_smoother(32, 5), d.set_noise_score_selector(1.5)),
+         O.Settings(smoothing_iterations=32, smoothing_window=5, threshold=1.5)),
+        (lambda d: (d.set_moving_average_smoother(1, 5), d.set_noise_score_selector(4.0)),
+         O.Settings(smoothing_iterations=1, smoothing_window=5, threshold=4.0)),
     ]:
         dec = Deconvoluter()
         setup(dec)
@@ -989,6 +1004,11 @@ def test_small_path_is_one_launch_and_matches_general_path_and_oracle(monkeypatc
         general = dec.deconvolute_spectra(ok)
         monkeypatch.delenv("MDB_SMALL_PATH")
         _same_results(small, general, "small batch vs general")
+        if settings.smoothing_kind != O.SMOOTH_IDENTITY and settings.smoothing_window in (3, 5, 7):
+            monkeypatch.setenv("MDB_STREAM_GENERIC", "1")  # the any-window interior loop on the same inputs
+            generic = dec.deconvolute_spectra(ok)
+            monkeypatch.delenv("MDB_STREAM_GENERIC")
+            _same_results(small, generic, "small batch, specialised vs any-window smoothing loop")
 
 
 def test_small_path_dense_peaks_short_inputs_and_errors():

@@ -11,7 +11,7 @@ from metabodecon_rust_b200 import Deconvoluter, Spectrum  # noqa: E402
 
 G = os.path.join(ROOT, "tests", "golden", "bruker")
 sim = Spectrum.read_bruker(os.path.join(G, "sim_01"), 10, 10, (3.34, 3.56))
-for iters, window in [(3, 3), (1, 3), (2, 3), (6, 3), (3, 7)]:
+for iters, window in [(2, 5), (1, 5), (2, 3), (3, 7)]:
     dec = Deconvoluter()
     dec.set_moving_average_smoother(iters, window)
     print(f"iterations={iters} window={window}", file=sys.stderr, flush=True)
