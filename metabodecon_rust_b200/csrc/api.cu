@@ -881,6 +881,15 @@ static bool stream_generic_env()
     const char *env = std::getenv("MDB_STREAM_GENERIC");
     return env && env[0] == '1';
 }
+// MDB_FIT_BLOCK=1 (experiment, tested): chunks of spectra with up to 1 024 peaks run every refinement pass in ONE
+// launch, one CTA per spectrum (fit_block_kernel).  Bit-identical, but measured 5 % slower on config 3 (4 000
+// spectra: 38.0 k against 40.0 k spectra/s, profiles/sweep_r2.txt): CTAs that hold their SM for a millisecond
+// interleave worse with the MSE kernels of the other chunks than many short one-warp CTAs do.
+static bool fit_block_enabled()
+{
+    const char *env = std::getenv("MDB_FIT_BLOCK");
+    return env && env[0] == '1';
+}
 static bool sup_quad()
 {
     const char *env = std::getenv("MDB_SUP_GROUP");
@@ -1336,6 +1345,21 @@ static mdb_status stage_b(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
                     CUDA_TRY(counted_memcpy_async(trace + (size_t)(it + 1) * n_trace, (it & 1) ? st.pa : st.pb, n_trace * 24,
                                              cudaMemcpyDeviceToHost, sb));
             }
+        } else if (!trace && !(persistent && persistent[0] == '1') && iters > 0 && ck.max_peaks <= FIT_BLOCK_MAX && fit_block_enabled()) {
+            // spectra with up to 1 024 selected peaks: one CTA per spectrum, every pass in ONE launch (fit_block_kernel)
+            double evals = 0.0;
+            for (size_t s = 0; s < S; ++s) evals += 3.0 * (double)ck.fdesc[s].n_iters * (double)ck.fdesc[s].n_peaks * (double)ck.fdesc[s].n_peaks;
+            const int threads = (int)align_up((size_t)std::max(ck.max_peaks, 1), 32);
+            const size_t smem = fit_block_smem_bytes(threads);
+            // launch-bound classes: up to 320 threads x 3 CTAs per SM, up to 576 x 2, up to 1 024 x 1
+            auto kern = dc.fit_arith == MDB_FIT_ULP ? fit_block_kernel<2, FIT_BLOCK_MAX, 1> : dc.fit_arith == MDB_FIT_CORRECTED ? fit_block_kernel<3, FIT_BLOCK_MAX, 1> : fit_block_kernel<1, FIT_BLOCK_MAX, 1>;
+            if (dc.fit_arith == MDB_FIT_EXACT && threads <= 320) kern = fit_block_kernel<1, 320, 3>;
+            else if (dc.fit_arith == MDB_FIT_EXACT && threads <= 576) kern = fit_block_kernel<1, 576, 2>;
+            if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fit_block_smem_bytes(FIT_BLOCK_MAX)));
+            prof_begin(&ck.spans, MDB_KERNEL_FIT_ITER, sb);
+            kern<<<(unsigned)S, threads, smem, sb>>>(d_fd, st);
+            LAUNCH_CHECK();
+            prof_end(&ck.spans, sb, evals);
         } else if (trace || !(persistent && persistent[0] == '1')) {
             // one launch per refinement pass (needed for the per-pass trace of mdb_stage_fit)
             for (int it = 0; it < iters; ++it) {

@@ -327,3 +327,40 @@ def test_measured_fp64_rate_is_plausible():
     assert lib.mdb_measure_fp64_rate(C.byref(dfma), C.byref(dadd)) == 0, _lib.last_error()
     # a B200 issues 148 x 64 FP64 instructions per clock at up to 1.965 GHz = 1.86e13/s
     assert 0.5e13 < dfma.value < 2.0e13 and 0.5e13 < dadd.value < 2.0e13
+
+
+@pytest.mark.parametrize("k_lor,n,count,fit_iters", [(60, 16384, 200, 10), (500, 131072, 150, 10), (900, 131072, 150, 3)])
+def test_all_refinement_passes_in_one_launch_match_one_launch_per_pass(k_lor, n, count, fit_iters, monkeypatch):
+    """Experiment kept under test (MDB_FIT_BLOCK=1; measured slower in the pipeline): chunks
+    whose spectra have at most 1 024 selected peaks run K6 as ONE launch, one CTA per spectrum, the parameter set
+    in shared memory (fit_block_kernel; launch-bound classes of 320, 576 and 1 024 threads); the product keeps
+    one launch per pass (fit_iter_kernel).  Same bits, and the oracle's
+    (fitter_analytical.rs:39-69), including spectra with different peak counts in one chunk and an empty one."""
+    x = synth.axis(n)
+    base = [fast_spectrum(7000 + 31 * k_lor + s, n=n, k=k_lor + 7 * s, x=x, integer=bool(s & 1)) for s in range(6)]
+    flat = np.full(n, 1000.0)  # no peaks at all: its CTA has nothing to do
+    ys = [base[s % 6] for s in range(count - 1)] + [flat]
+    specs = [Spectrum(x, y, SB) for y in ys]
+    dec = Deconvoluter()
+    dec.set_analytical_fitter(fit_iters)
+    dec.set_superposition_mode("exact")
+    lib = _lib.load()
+    monkeypatch.setenv("MDB_FIT_BLOCK", "1")
+    lib.mdb_reset_kernel_launch_count()
+    block = dec.deconvolute_spectra(specs[:-1])
+    launches_block = lib.mdb_kernel_launch_count()
+    monkeypatch.delenv("MDB_FIT_BLOCK")
+    lib.mdb_reset_kernel_launch_count()
+    per_pass = dec.deconvolute_spectra(specs[:-1])
+    launches_per_pass = lib.mdb_kernel_launch_count()
+    assert launches_block < launches_per_pass  # the passes really went into one launch per chunk
+    for i, (a, b) in enumerate(zip(block, per_pass)):
+        assert np.array_equal(a.peaks, b.peaks), i
+        assert_same_bits(a.parameters, b.parameters, f"spectrum {i}")
+        assert a.mse == b.mse
+    settings = O.Settings(fitting_iterations=fit_iters)
+    check_vs_oracle(block[:6], specs[:6], settings, what=f"fit_block k={k_lor}")
+    assert max(len(o.peaks) for o in block) <= 1024
+    # the spectrum without peaks is an error in the reference (EmptySignalRegion / no peaks); it must not disturb the others
+    with pytest.raises(Exception):
+        dec.deconvolute_spectra(specs)
