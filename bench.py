@@ -149,6 +149,20 @@ def workload_name(args):
     return (f"{args.workload}: batch of {args.total_spectra} {desc}, sharded over the GPUs (strong scaling)")
 
 
+def workload_config(args, world):
+    """The `config` object of the JSON line: a pure description of the workload, IDENTICAL for the GPU arm and for
+    --impl reference at the same --gpus (measured statistics live in `workload_stats`, what a step of the
+    reference arm actually timed in its `cpu_baseline.sample`)."""
+    total = args.total_spectra
+    per_gpu = total // world  # rank 0's shard: [0, total // world)
+    return {"workload": workload_name(args), "points": N_POINTS, "total_spectra": total,
+            "spectra_per_gpu_per_step": per_gpu, "settings": "Deconvoluter::default()",
+            "superposition_mode": args.superposition,
+            "parallelism": f"the {total} spectra cut into {world} contiguous shard(s), one process per GPU, no collective",
+            "inputs": "host PCG64 parameters + noise per spectrum, exact ordered superposition for the signal (the same arrays for the GPU arm, its cpu_baseline and --impl reference)",
+            "l2": f"inputs {per_gpu * N_POINTS * 8 / 2**20:.0f} MiB per GPU per step, larger than the 126 MB L2"}
+
+
 def sample_indices(total, count):
     """`count` spectrum indices spread over [0, total): the sample is drawn across the batch."""
     count = max(1, min(count, total))
@@ -190,9 +204,8 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "spectra/s deconvolved (2^17 pts)", "value": value, "unit": "spectra/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args), "points": N_POINTS, "total_spectra": args.total_spectra,
-                   "spectra_per_step_timed": len(idx), "mean_selected_peaks": float(np.mean(nsel)),
-                   "settings": "Deconvoluter::default()"},
+        "config": workload_config(args, world),
+        "workload_stats": {"spectra_per_step_timed": len(idx), "mean_selected_peaks": float(np.mean(nsel))},
         "cpu_baseline": {"value": value, "unit": "spectra/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "spectra/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "clocks": None,
@@ -903,12 +916,8 @@ def main():
         "metric": "spectra/s deconvolved (2^17 pts)", "value": value, "unit": "spectra/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args), "points": N_POINTS, "total_spectra": TOTAL,
-                   "spectra_per_gpu_per_step": S, "mean_selected_peaks": total_peaks / TOTAL, "mean_lorentzians": total_lor / TOTAL,
-                   "settings": "Deconvoluter::default()", "superposition_mode": args.superposition,
-                   "parallelism": f"the {TOTAL} spectra cut into {world} contiguous shard(s), one process per GPU, no collective",
-                   "inputs": "host PCG64 parameters + noise per spectrum, exact ordered superposition for the signal (same arrays as --impl reference)",
-                   "l2": f"inputs {S * N_POINTS * 8 / 2**20:.0f} MiB per GPU per step, larger than the 126 MB L2"},
+        "config": workload_config(args, world),
+        "workload_stats": {"mean_selected_peaks": total_peaks / TOTAL, "mean_lorentzians": total_lor / TOTAL},
         "e2e": e2e, "e2e_pageable": e2e_pageable, "e2e_one_call": one_call,
         "gpu_launches": int(launches_all), "clocks": clocks, "fp64_measured": fp64_measured,
         "roofline": roofline, "roofline_other_fp64": other, "pipeline_fp64": overall,
