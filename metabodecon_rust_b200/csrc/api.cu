@@ -918,7 +918,9 @@ static mdb_status launch_smooth(cudaStream_t stream, const SpecDesc *d_desc, con
     // the chunk pipeline (40+ spectra per chunk, eight chunks in flight) would crowd the FP64 kernels
     // of the other chunks off the SMs; there the lane-packed kernel (10 chains per warp) stays.
     const char *stream_env = std::getenv("MDB_SMOOTH_STREAM");
-    bool streamable = iters >= 1 && iters <= STREAM_MAX_ITERS && window >= 1 && window <= 64 && S <= 32
+    size_t stream_max = 32;
+    if (const char *env = std::getenv("MDB_STREAM_MAX_SPECTRA")) if (std::atoi(env) >= 1) stream_max = (size_t)std::atoi(env);  // sweeps
+    bool streamable = iters >= 1 && iters <= STREAM_MAX_ITERS && window >= 1 && window <= 64 && S <= stream_max
                       && !(stream_env && stream_env[0] == '0') && !(force && force[0] == '1');
     for (const SpecDesc &d : descs) streamable = streamable && d.n >= 4096;
     prof_begin(spans, MDB_KERNEL_SMOOTH, stream);
