@@ -1088,7 +1088,7 @@ static mdb_status stage_a(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
             double *stage = ws.h_stage.as<double>();
             CUDA_TRY(cudaStreamSynchronize(sc));  // the previous DMA out of this staging area has finished
             for (size_t s = 0; s < S; ++s)
-                std::memcpy(stage + y_off[s], hs[ck.first + s].y, hs[ck.first + s].n * 8);
+                mdb_host_row_copy(stage + y_off[s], hs[ck.first + s].y, hs[ck.first + s].n);
             CUDA_TRY(counted_memcpy_async(y_dst, stage, y_elems * 8, cudaMemcpyHostToDevice, sc));
         } else {
             size_t s = 0;
@@ -1700,10 +1700,15 @@ static mdb_status run_pipeline(const mdb_deconvoluter &dc, const std::vector<Hos
         size_t bytes = 0;
         for (auto &h : hs) bytes += h.n * 8;
         const unsigned hw = std::max(2u, std::thread::hardware_concurrency());
-        size_t n_thr = std::max<size_t>(1, std::min<size_t>(8, hw / 2 / (unsigned)std::max(1, t_pipeline_peers)));
+        // pipelines sharing this host's cores: the in-process sharder's threads, or the other ranks of a torchrun job
+        // (LOCAL_WORLD_SIZE) -- eight processes with eight gather threads each oversubscribed a 32-thread host
+        int peers = std::max(1, t_pipeline_peers);
+        if (const char *lws = std::getenv("LOCAL_WORLD_SIZE")) peers = std::max(peers, std::atoi(lws));
+        size_t n_thr = std::max<size_t>(2, std::min<size_t>(8, hw / 2 / (unsigned)peers));
         if (const char *env = std::getenv("MDB_STAGE_THREADS")) if (std::atoi(env) >= 1) n_thr = (size_t)std::min(std::atoi(env), 64);
-        if (bytes < ((size_t)4 << 20)) n_thr = 1;  // small calls: one helper is plenty
-        stager.reset(new Stager(n_thr));
+        // small calls (one blood spectrum is 1 MB): stage A gathers the rows on the calling thread -- starting and
+        // joining a helper thread costs more than the copy
+        if (bytes >= ((size_t)4 << 20)) stager.reset(new Stager(n_thr));
     }
     // Chunk size: starts at chunk_size_for() and, unless pinned by MDB_CHUNK_SPECTRA, is re-derived
     // from the first chunk's selected-peak counts so that a chunk carries about TARGET Lorentzian
