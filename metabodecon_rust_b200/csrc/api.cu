@@ -10,6 +10,7 @@
 #include "smooth_lanes.cuh"
 #include "small_fused.cuh"
 #include "smooth_stream.cuh"
+#include "smooth_split.cuh"
 #include "fit_wide.cuh"
 
 #include <algorithm>
@@ -925,6 +926,18 @@ static mdb_status launch_smooth(cudaStream_t stream, const SpecDesc *d_desc, con
     for (const SpecDesc &d : descs) streamable = streamable && d.n >= 4096;
     prof_begin(spans, MDB_KERNEL_SMOOTH, stream);
     if (streamable) {
+        // windows 3, 5, 7 and up to six passes: one chain warp per pass, the multiply done by the mover warps (smooth_split.cuh)
+        const char *split_env = std::getenv("MDB_SMOOTH_SPLIT");
+        if ((window == 3 || window == 5 || window == 7) && iters <= SPLIT_MAX_ITERS && !stream_generic_env()
+            && !(split_env && split_env[0] == '0')) {
+            auto kern = window == 5 ? smooth_split_kernel<5> : window == 3 ? smooth_split_kernel<3> : smooth_split_kernel<7>;
+            const size_t smem = smooth_split_smem_bytes(iters);
+            CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smooth_split_smem_bytes(SPLIT_MAX_ITERS)));
+            kern<<<(unsigned)S, smooth_split_threads(iters), smem, stream>>>(d_desc, iters);
+            LAUNCH_CHECK();
+            prof_end(spans, stream, 16.0 * pts);  // algorithmic bytes: read 8N + write 8N
+            return MDB_OK;
+        }
         const size_t smem = smooth_stream_smem_bytes(iters);
         // interior loop specialised for the default window and the ones optimize_settings tries (smooth_stream.cuh)
         auto kern = window == 5 ? smooth_stream_kernel<5> : window == 3 ? smooth_stream_kernel<3> : window == 7 ? smooth_stream_kernel<7> : smooth_stream_kernel<0>;

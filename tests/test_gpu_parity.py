@@ -272,11 +272,17 @@ def test_smoothing_stream_kernel_ring_edges(n, monkeypatch):
     yi = np.rint(y)
     # windows 3, 5 and 7 take the interior loop specialised on the window (register-resident blocks, stores
     # one round late); MDB_STREAM_GENERIC=1 sends them through the any-window loop as well
-    for it, w in [(3, 3), (1, 2), (2, 2), (12, 3), (5, 8), (4, 9), (2, 33), (3, 64), (1, 7), (2, 5), (12, 5), (7, 7), (1, 5)]:
+    # and with at most six passes they run one chain warp per pass with the multiply taken off the chain
+    # (smooth_split.cuh) unless MDB_SMOOTH_SPLIT=0
+    for it, w in [(3, 3), (1, 2), (2, 2), (12, 3), (5, 8), (4, 9), (2, 33), (3, 64), (1, 7), (2, 5), (12, 5), (7, 7), (1, 5),
+                  (6, 5), (4, 7), (6, 3)]:
         want = O.smooth_values(y, it, w)
         assert_bit_equal(gpu_smooth(y, it, w), want, f"stream n={n} ({it},{w})")
         assert_bit_equal(gpu_smooth(yi, it, w), O.smooth_values(yi, it, w), f"stream n={n} ({it},{w}) integer")
         if w in (3, 5, 7):
+            monkeypatch.setenv("MDB_SMOOTH_SPLIT", "0")
+            assert_bit_equal(gpu_smooth(y, it, w), want, f"stream, one warp for all passes n={n} ({it},{w})")
+            monkeypatch.delenv("MDB_SMOOTH_SPLIT")
             monkeypatch.setenv("MDB_STREAM_GENERIC", "1")
             assert_bit_equal(gpu_smooth(y, it, w), want, f"stream, any-window loop n={n} ({it},{w})")
             monkeypatch.delenv("MDB_STREAM_GENERIC")
