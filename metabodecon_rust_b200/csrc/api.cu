@@ -840,6 +840,7 @@ struct Chunk {
     bool stage_b_launched = false, finished = false;
     double est_evals = 0.0;            // Lorentzian evaluations of this chunk's fit + MSE kernels (from the counts)
     std::shared_ptr<StageJob> stage_job;  // pageable host rows being gathered into ws->h_stage (null: none)
+    bool startup = false;                 // one of the first chunks of a call: its stage A runs on an otherwise idle GPU
     // Streams of this chunk (null: the workspace's own).  The pipeline hands out streams from a small
     // per-call set (PipeStreams) instead of one pair per workspace, see run_pipeline.
     cudaStream_t s_copy = nullptr, s_a = nullptr, s_b = nullptr, s_m = nullptr;
@@ -902,7 +903,7 @@ static int sm_count() { return device_info().sms; }
 // K1 dispatch: the lane-per-pass TMA-staged kernel when the settings are covered (window 2..9,
 // up to 32 iterations) and every input row is 16-byte aligned, else one generic pass per launch.
 static mdb_status launch_smooth(cudaStream_t stream, const SpecDesc *d_desc, const std::vector<SpecDesc> &descs,
-                                int iters, int window, std::vector<ProfSpan> *spans)
+                                int iters, int window, std::vector<ProfSpan> *spans, size_t latency_form_up_to = 32)
 {
     const size_t S = descs.size();
     double pts = 0.0;
@@ -919,7 +920,7 @@ static mdb_status launch_smooth(cudaStream_t stream, const SpecDesc *d_desc, con
     // the chunk pipeline (40+ spectra per chunk, eight chunks in flight) would crowd the FP64 kernels
     // of the other chunks off the SMs; there the lane-packed kernel (10 chains per warp) stays.
     const char *stream_env = std::getenv("MDB_SMOOTH_STREAM");
-    size_t stream_max = 32;
+    size_t stream_max = latency_form_up_to;
     if (const char *env = std::getenv("MDB_STREAM_MAX_SPECTRA")) if (std::atoi(env) >= 1) stream_max = (size_t)std::atoi(env);  // sweeps
     bool streamable = iters >= 1 && iters <= STREAM_MAX_ITERS && window >= 1 && window <= 64 && S <= stream_max
                       && !(stream_env && stream_env[0] == '0') && !(force && force[0] == '1');
@@ -1144,8 +1145,13 @@ static mdb_status stage_a(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
     // ---- K1 smoothing (deconvoluter.rs:531-532)
     if (!skip_smoothing_input_is_smoothed && !preset) {
         if (ma) {
+            // The first chunks of a call smooth on an idle GPU: there the latency form (1.4 ms per launch instead of
+            // 2.9, one CTA per spectrum) brings the first peak counts -- and with them the first FP64 work -- forward;
+            // later chunks keep the lane-packed kernel, whose few warps do not crowd the fit / MSE kernels.
+            const char *su = std::getenv("MDB_STARTUP_STREAM");
+            const size_t up_to = (ck.startup && !(su && su[0] == '0')) ? 80 : 32;
             mdb_status sst = launch_smooth(sa, d_desc, ck.desc, (int)dc.smoothing.iterations,
-                                           (int)dc.smoothing.window_size, &ck.spans);
+                                           (int)dc.smoothing.window_size, &ck.spans, up_to);
             if (sst != MDB_OK) return sst;
         } else {  // Identity (smoothing/identity.rs): the smoothed copy is the input itself
             for (size_t s = 0; s < S; ++s)
@@ -1777,6 +1783,7 @@ static mdb_status run_pipeline(const mdb_deconvoluter &dc, const std::vector<Hos
         ck.ev_in = pipe->ev_in[k % ring];
         ck.ev_fit = pipe->ev_fit[k % ring];
         ck.first = next_first;
+        ck.startup = !serial && k <= ahead;  // the start-up burst (see stage_a: latency form of the smoothing kernel)
         size_t count = std::min(csz, n_spectra - next_first);
         if (n_spectra - next_first - count < csz / 4) count = n_spectra - next_first;  // no tiny straggler chunk
         ck.count = count;
