@@ -1340,13 +1340,18 @@ static mdb_status stage_b(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
             dim3 grid3(grid.x, grid.y, 3);
             // MDB_FIT_WIDE=1 selects the instruction-parallel form (8 Lorentzians per thread), anything else
             // the thread-parallel one (producers / accumulators)
-            // (its 512-thread, 57 KB CTAs pay off while they all fit the GPU at once: one blood spectrum is 48
-            // of them; sixteen spectra are 768, and the 128-thread instruction-parallel form is faster again)
+            // (its 256-thread CTAs pay off while they all fit the GPU at once: one blood spectrum is 93 of them;
+            // sixteen spectra are ~1 500, and the 128-thread instruction-parallel form is faster again)
             long long wide2_ctas = 0;
             for (size_t s = 0; s < S; ++s) wide2_ctas += 3ll * ((ck.fdesc[s].n_peaks + WIDE2_CHAINS - 1) / WIDE2_CHAINS);
-            const bool wide2 = !(wide_env && wide_env[0] == '1') && wide2_ctas <= 2ll * sm_count();
+            const bool wide2 = !(wide_env && wide_env[0] == '1') && wide2_ctas <= 4ll * sm_count();
+            // the whole parameter set of a spectrum behind the quotient buffers when it fits (up to ~4 000 peaks)
+            const size_t wide2_params = align_up((size_t)std::max(ck.max_peaks, 1) * 24, 16);
+            const bool wide2_psm = wide2 && WIDE2_SMEM + wide2_params <= (size_t)160 * 1024 && !std::getenv("MDB_WIDE2_GLOBAL_PARAMS");
+            const size_t wide2_smem = WIDE2_SMEM + (wide2_psm ? wide2_params : 0);
             if (wide2)
-                CUDA_TRY(cudaFuncSetAttribute(fit_wide2_superpose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WIDE2_SMEM));
+                CUDA_TRY(cudaFuncSetAttribute(wide2_psm ? fit_wide2_superpose_kernel<true> : fit_wide2_superpose_kernel<false>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide2_smem));
             for (int it = 0; it < iters; ++it) {
                 double evals = 0.0;
                 for (size_t s = 0; s < S; ++s)
@@ -1354,7 +1359,8 @@ static mdb_status stage_b(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
                 prof_begin(&ck.spans, MDB_KERNEL_FIT_ITER, sb);
                 if (wide2) {
                     dim3 g2((unsigned)((ck.max_peaks + WIDE2_CHAINS - 1) / WIDE2_CHAINS), (unsigned)S, 3);
-                    fit_wide2_superpose_kernel<<<g2, WIDE2_THREADS, WIDE2_SMEM, sb>>>(d_fd, st, yn, yn_stride, it);
+                    if (wide2_psm) fit_wide2_superpose_kernel<true><<<g2, WIDE2_THREADS, wide2_smem, sb>>>(d_fd, st, yn, yn_stride, it);
+                    else fit_wide2_superpose_kernel<false><<<g2, WIDE2_THREADS, wide2_smem, sb>>>(d_fd, st, yn, yn_stride, it);
                 } else {
                     fit_wide_superpose_kernel<<<grid3, FIT_THREADS, LOR_SMEM_BYTES, sb>>>(d_fd, st, yn, yn_stride, it);
                 }

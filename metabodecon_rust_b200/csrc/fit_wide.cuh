@@ -134,13 +134,27 @@ fit_wide_superpose_kernel(const FitDesc *__restrict__ fd, FitState st, double *_
 // quotients then keep ~50 SMs x 14 producer warps busy instead of 24 SMs x 4 warps of 8-deep ILP.
 // Every quotient and every addition is the same operation as in fit_iter_kernel.
 // ---------------------------------------------------------------------------------------------
-constexpr int WIDE2_CHAINS = 64;
-constexpr int WIDE2_PHASES = 7;
+// Round 2 shape: 32 chains per CTA (one warp wide), eight warps.  Warp 0 holds the 32 accumulator threads, warps
+// 1-3 and 5-7 are the producers of phases 0-5 (48 Lorentzians per tile), warp 4 exits: warps are dealt to the
+// SM's four schedulers by warp index modulo 4, so the accumulator warp has scheduler 0 -- and its FP64 issue
+// slots -- to itself, and its chain of dependent additions (the critical path: P additions of 8.2 cycles each)
+// is not queued behind the producers' divisions.  Half the chains per CTA also spreads one blood spectrum over
+// 93 SMs instead of 48.  (64 chains x 7 producer phases in 16 warps, the round-1 shape: 30 us per pass; with the
+// parameters in shared memory 22 us; this shape: see DESIGN.md section 4.)
+constexpr int WIDE2_CHAINS = 32;
+constexpr int WIDE2_PHASES = 6;
 constexpr int WIDE2_TILE = 8 * WIDE2_PHASES;                          // Lorentzians per tile
-constexpr int WIDE2_THREADS = WIDE2_CHAINS * (1 + WIDE2_PHASES);      // 64 accumulators + 448 producers
+constexpr int WIDE2_THREADS = 8 * 32;                                 // warp 0: accumulators, 1-3 / 5-7: producers, 4: idle
+constexpr int WIDE2_BAR_THREADS = (1 + WIDE2_PHASES) * 32;            // threads that take part in the named barriers
 constexpr size_t WIDE2_SMEM = (size_t)2 * WIDE2_TILE * WIDE2_CHAINS * sizeof(double);
 
+// PARAMS_IN_SMEM: the spectrum's whole parameter set (24 bytes per Lorentzian) is copied into shared memory once,
+// behind the quotient buffers, and the producers read their eight Lorentzians per tile from there.  With the
+// parameters fetched from L2 at the start of every tile the producers -- which move in lockstep with the tile
+// barriers -- spent more time waiting for those loads than computing (ncu, blood_01: long-scoreboard stalls on
+// top, FP64 pipe 31 % of active cycles, 30 us per pass).
 // grid (ceil(max_peaks / WIDE2_CHAINS), spectra, 3): blockIdx.z is the stencil point
+template <bool PARAMS_IN_SMEM>
 __global__ void __launch_bounds__(WIDE2_THREADS)
 fit_wide2_superpose_kernel(const FitDesc *__restrict__ fd, FitState st, double *__restrict__ yn, long long yn_stride, int it)
 {
@@ -149,23 +163,42 @@ fit_wide2_superpose_kernel(const FitDesc *__restrict__ fd, FitState st, double *
     const FitDesc f = fd[blockIdx.y];
     if (blockIdx.x * WIDE2_CHAINS >= f.n_peaks || it >= f.n_iters) return;
     const double *__restrict__ pin = ((it & 1) ? st.pb : st.pa) + 3 * f.off;
+    const double *sp = reinterpret_cast<const double *>(wide2_smem + WIDE2_SMEM);  // the parameter set (PARAMS_IN_SMEM)
+    if (PARAMS_IN_SMEM) {
+        double *w = reinterpret_cast<double *>(wide2_smem + WIDE2_SMEM);
+        for (int i = threadIdx.x; i < 3 * f.n_peaks; i += WIDE2_THREADS) w[i] = __ldcg(pin + i);  // L2: written by the last solve launch
+        __syncthreads();
+    }
     const int q = blockIdx.z;
     const double *__restrict__ ox = q == 0 ? st.ox1 : (q == 1 ? st.ox2 : st.ox3);
-    const int c = threadIdx.x % WIDE2_CHAINS, role = threadIdx.x / WIDE2_CHAINS;   // role 0: accumulator
+    const int c = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (warp == 4) return;                                            // leaves scheduler 0 to the accumulator warp
+    const int role = warp == 0 ? 0 : (warp < 4 ? warp : warp - 1);    // 0: accumulator, 1..6: producer of phase role - 1
     const int k = blockIdx.x * WIDE2_CHAINS + c;
     const bool active = k < f.n_peaks;
     const long long g = f.off + (active ? k : 0);
     const int P = f.n_peaks;
     const int n_tiles = (P + WIDE2_TILE - 1) / WIDE2_TILE;
-    // named barriers 1, 2: full[0], full[1]; 3, 4: empty[0], empty[1]; every use counts all threads
-    auto bar_sync = [](int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(WIDE2_THREADS) : "memory"); };
-    auto bar_arrive = [](int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(WIDE2_THREADS) : "memory"); };
+    // named barriers 1, 2: full[0], full[1]; 3, 4: empty[0], empty[1]; every use counts the seven working warps
+    auto bar_sync = [](int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(WIDE2_BAR_THREADS) : "memory"); };
+    auto bar_arrive = [](int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(WIDE2_BAR_THREADS) : "memory"); };
     if (role == 0) {
         double acc = 0.0;
         for (int t = 0; t < n_tiles; ++t) {
             const int b = t & 1, cnt = min(WIDE2_TILE, P - t * WIDE2_TILE);
             bar_sync(1 + b);                                          // tile t is in buffer b
             const double *src = quot + ((size_t)b * WIDE2_TILE) * WIDE2_CHAINS + c;
+            if (cnt == WIDE2_TILE) {
+                // a full tile: all 48 quotients are fetched up front (independent loads, one latency), so the chain of
+                // additions never waits for shared memory
+                double v[WIDE2_TILE];
+#pragma unroll
+                for (int u = 0; u < WIDE2_TILE; ++u) v[u] = src[(size_t)u * WIDE2_CHAINS];
+                bar_arrive(3 + b);                                    // buffer b may be refilled: its values are in registers
+#pragma unroll
+                for (int u = 0; u < WIDE2_TILE; ++u) acc = __dadd_rn(acc, v[u]);
+                continue;
+            }
             int jj = 0;
             for (; jj + 8 <= cnt; jj += 8) {
                 double v[8];
@@ -193,8 +226,13 @@ fit_wide2_superpose_kernel(const FitDesc *__restrict__ fd, FitState st, double *
             double *dst = quot + ((size_t)b * WIDE2_TILE + ph * 8) * WIDE2_CHAINS + c;
             if (j0 + 8 <= P) {
                 double prm[24];
+                if (PARAMS_IN_SMEM) {
 #pragma unroll
-                for (int i = 0; i < 24; ++i) prm[i] = __ldg(pin + 3 * j0 + i);
+                    for (int i = 0; i < 24; ++i) prm[i] = sp[3 * j0 + i];
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 24; ++i) prm[i] = __ldg(pin + 3 * j0 + i);
+                }
                 bool ok = x_ok;
 #pragma unroll
                 for (int u = 0; u < 8; ++u) ok = ok && params_fast_domain(prm[3 * u], prm[3 * u + 1], prm[3 * u + 2]);
