@@ -1400,7 +1400,7 @@ static mdb_status stage_b(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
                 if (const char *env = std::getenv("MDB_FIT_CTA")) { const int v = std::atoi(env); if (v == 32 || v == FIT_THREADS) cta = v; }
                 auto fit_kern = dc.fit_arith == MDB_FIT_ULP ? fit_iter_kernel<2> : dc.fit_arith == MDB_FIT_CORRECTED ? fit_iter_kernel<3> : fit_iter_kernel<1>;
                 if (cta == 32)
-                    fit_kern = dc.fit_arith == MDB_FIT_ULP ? fit_iter_kernel<2, 32, 128> : dc.fit_arith == MDB_FIT_CORRECTED ? fit_iter_kernel<3, 32, 128> : fit_iter_kernel<1, 32, 128>;
+                    fit_kern = dc.fit_arith == MDB_FIT_ULP ? fit_iter_kernel<2, 32, 128, 32> : dc.fit_arith == MDB_FIT_CORRECTED ? fit_iter_kernel<3, 32, 128, 32> : fit_iter_kernel<1, 32, 128, 32>;
                 size_t fit_smem = cta == 32 ? fit_smem_bytes(128) : LOR_SMEM_BYTES;
                 if (const char *occ = std::getenv("MDB_FIT_OCC")) {  // experiment: 12 CTAs of 128 threads per SM (<= 40 registers, 256-Lorentzian tiles)
                     if (occ[0] == '1' && cta == FIT_THREADS && dc.fit_arith == MDB_FIT_EXACT) { fit_kern = fit_iter_kernel<1, 128, 256, 12>; fit_smem = fit_smem_bytes(256); }
