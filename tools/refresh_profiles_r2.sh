@@ -24,6 +24,9 @@ $B3 > gpurun_out/p3.json 2> gpurun_out/p3.err || { tail -5 gpurun_out/p3.err; ex
 full fit_iter_config3 fit_iter_kernel 25 $B3
 unset MDB_CHUNK_SPECTRA
 python tools/run_sup_once.py > gpurun_out/sup_once.log 2>&1 && full superposition_vec "superposition_kernel<.int.0," 1 python tools/run_sup_once.py
-python tools/run_blood_once.py > gpurun_out/blood_once.log 2>&1 && full smooth_stream smooth_stream_kernel 1 python tools/run_blood_once.py
+python tools/run_blood_once.py > gpurun_out/blood_once.log 2>&1 && full smooth_split smooth_split_kernel 1 python tools/run_blood_once.py
+MDB_SMOOTH_SPLIT=0 full smooth_stream smooth_stream_kernel 1 python tools/run_blood_once.py
+full fit_wide2 fit_wide2_superpose_kernel 12 python tools/run_blood_once.py
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_blood_r2.csv python tools/run_blood_once.py > /dev/null 2>&1
 python tools/run_sim_once.py > gpurun_out/sim_once.log 2>&1 && full small_fused small_fused_kernel 1 python tools/run_sim_once.py
 ls -la gpurun_out/*_r2.ncu-rep
