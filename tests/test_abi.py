@@ -317,3 +317,19 @@ def test_spectrum_json_and_messagepack_round_trip(tmp_path):
     (tmp_path / "bad.json").write_text('{"size": 3}')
     with pytest.raises(exceptions.SerializationError):
         Spectrum.read_json(str(tmp_path / "bad.json"))
+
+
+def test_integration_doc_names_every_header_symbol_and_nothing_else():
+    """INTEGRATION.md is the map from the reference's interfaces to the C ABI: every function the header
+    declares appears there, and every mdb_* function name used there exists in the header."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with open(os.path.join(root, "include", "mdb200.h")) as fh:
+        header = fh.read()
+    with open(os.path.join(root, "INTEGRATION.md")) as fh:
+        doc = fh.read()
+    declared = set(re.findall(r"\b(mdb_[a-z0-9_]+)\s*\(", header))
+    for name in sorted(declared):
+        assert re.search(r"\b%s\b" % name, doc), f"{name} is declared in include/mdb200.h but INTEGRATION.md does not mention it"
+    for name in sorted(set(re.findall(r"\bmdb_[a-z0-9_]*[a-z0-9]\b", doc))):
+        assert re.search(r"\b%s\b" % name, header), f"INTEGRATION.md mentions {name}, which include/mdb200.h does not know"
