@@ -25,6 +25,7 @@
 // its oldest element sits exactly in the slot about to be overwritten and, with the step loop
 // unrolled by W, ring slots are addressed statically (registers).
 #pragma once
+#include <cstdlib>
 #include "kernels.cuh"
 
 namespace mdb {
@@ -342,6 +343,9 @@ inline SmoothLanesFn smooth_lanes_lookup(int window, int iterations, size_t n_sp
     const size_t warps = (n_spectra + (size_t)(32 / iterations) - 1) / (size_t)(32 / iterations);
     const int lag = (window / 2) + (iterations - 1) * (window + window / 2);  // L = r + (I-1)(W+r) must fit a tile
     int cls = (iterations >= 3 && warps <= (size_t)sm_count) ? 0 : (iterations >= 3 && warps > (size_t)3 * sm_count) ? 2 : 1;
+    if (const char *env = std::getenv("MDB_SMOOTH_CLASS")) {  // sweeps: force a tile class (0: 224 points / ~126 KB per warp, 1: 112, 2: 56 / ~28 KB)
+        if (env[0] >= '0' && env[0] <= '2' && iterations >= 3) cls = env[0] - '0';
+    }
 #define MDB_SL_CASE(Wv) \
     if (window == Wv) { \
         if (cls == 2 && lag > SmoothTile<Wv, 2>::T) cls = 1; \
