@@ -1352,6 +1352,14 @@ static mdb_status stage_b(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
             if (wide2)
                 CUDA_TRY(cudaFuncSetAttribute(wide2_psm ? fit_wide2_superpose_kernel<true> : fit_wide2_superpose_kernel<false>,
                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide2_smem));
+            // counters for the solve step fused into the producer / accumulator kernel (MDB_WIDE2_FUSED_SOLVE=0: separate launch)
+            int *wide2_done = nullptr;
+            if (wide2 && !(std::getenv("MDB_WIDE2_FUSED_SOLVE") && std::getenv("MDB_WIDE2_FUSED_SOLVE")[0] == '0')) {
+                const size_t n_counters = S * (size_t)((ck.max_peaks + WIDE2_CHAINS - 1) / WIDE2_CHAINS);
+                CUDA_TRY(ws.fit_queue.ensure(n_counters * 4));
+                CUDA_TRY(cudaMemsetAsync(ws.fit_queue.p, 0, n_counters * 4, sb));
+                wide2_done = ws.fit_queue.as<int>();
+            }
             for (int it = 0; it < iters; ++it) {
                 double evals = 0.0;
                 for (size_t s = 0; s < S; ++s)
@@ -1359,14 +1367,16 @@ static mdb_status stage_b(Chunk &ck, const std::vector<HostSpec> &hs, const mdb_
                 prof_begin(&ck.spans, MDB_KERNEL_FIT_ITER, sb);
                 if (wide2) {
                     dim3 g2((unsigned)((ck.max_peaks + WIDE2_CHAINS - 1) / WIDE2_CHAINS), (unsigned)S, 3);
-                    if (wide2_psm) fit_wide2_superpose_kernel<true><<<g2, WIDE2_THREADS, wide2_smem, sb>>>(d_fd, st, yn, yn_stride, it);
-                    else fit_wide2_superpose_kernel<false><<<g2, WIDE2_THREADS, wide2_smem, sb>>>(d_fd, st, yn, yn_stride, it);
+                    if (wide2_psm) fit_wide2_superpose_kernel<true><<<g2, WIDE2_THREADS, wide2_smem, sb>>>(d_fd, st, yn, yn_stride, it, wide2_done);
+                    else fit_wide2_superpose_kernel<false><<<g2, WIDE2_THREADS, wide2_smem, sb>>>(d_fd, st, yn, yn_stride, it, wide2_done);
                 } else {
                     fit_wide_superpose_kernel<<<grid3, FIT_THREADS, LOR_SMEM_BYTES, sb>>>(d_fd, st, yn, yn_stride, it);
                 }
                 LAUNCH_CHECK();
-                fit_wide_solve_kernel<<<grid, FIT_THREADS, 0, sb>>>(d_fd, st, yn, yn_stride, it);
-                LAUNCH_CHECK();
+                if (!wide2_done) {  // (the producer / accumulator kernel solves in its last CTA per peak block)
+                    fit_wide_solve_kernel<<<grid, FIT_THREADS, 0, sb>>>(d_fd, st, yn, yn_stride, it);
+                    LAUNCH_CHECK();
+                }
                 prof_end(&ck.spans, sb, evals);
                 if (trace)
                     CUDA_TRY(counted_memcpy_async(trace + (size_t)(it + 1) * n_trace, (it & 1) ? st.pa : st.pb, n_trace * 24,

@@ -154,9 +154,14 @@ constexpr size_t WIDE2_SMEM = (size_t)2 * WIDE2_TILE * WIDE2_CHAINS * sizeof(dou
 // barriers -- spent more time waiting for those loads than computing (ncu, blood_01: long-scoreboard stalls on
 // top, FP64 pipe 31 % of active cycles, 30 us per pass).
 // grid (ceil(max_peaks / WIDE2_CHAINS), spectra, 3): blockIdx.z is the stencil point
+// `done` (may be null): one counter per (spectrum, peak block).  The three CTAs of a peak block (one per stencil
+// point) each bump it once per pass when their rescaled stencil values are written; the CTA that draws the
+// third ticket finds all three values of its 32 peaks in memory and does the mirror + solve step itself
+// (fit_wide_solve_kernel's body), which saves a launch boundary per pass.  Counters only grow: ticket % 3.
 template <bool PARAMS_IN_SMEM>
 __global__ void __launch_bounds__(WIDE2_THREADS)
-fit_wide2_superpose_kernel(const FitDesc *__restrict__ fd, FitState st, double *__restrict__ yn, long long yn_stride, int it)
+fit_wide2_superpose_kernel(const FitDesc *__restrict__ fd, FitState st, double *__restrict__ yn, long long yn_stride, int it,
+                           int *__restrict__ done)
 {
     extern __shared__ __align__(16) unsigned char wide2_smem[];
     double *quot = reinterpret_cast<double *>(wide2_smem);            // [buffer][slot in tile][chain]
@@ -214,6 +219,27 @@ fit_wide2_superpose_kernel(const FitDesc *__restrict__ fd, FitState st, double *
             const double *__restrict__ oy = q == 0 ? st.oy1 : (q == 1 ? st.oy2 : st.oy3);
             const double *__restrict__ sy = q == 0 ? st.sy1 : (q == 1 ? st.sy2 : st.sy3);
             yn[(long long)q * yn_stride + g] = __dmul_rn(sy[g], __ddiv_rn(oy[g], acc));  // :42-54
+        }
+        if (done) {  // the whole accumulator warp is here (role 0 = warp 0)
+            __threadfence();  // this CTA's stencil values are visible before its ticket is
+            int ticket = 0;
+            if (c == 0) ticket = atomicAdd(&done[(size_t)blockIdx.y * gridDim.x + blockIdx.x], 1);
+            ticket = __shfl_sync(0xffffffffu, ticket, 0);
+            if (ticket % 3 == 2) {
+                __threadfence();
+                if (active) {  // fit_wide_solve_kernel, for this block's peaks
+                    double *__restrict__ pout = (it & 1) ? st.pa : st.pb;
+                    Stencil p;
+                    p.x1 = st.sx1[g]; p.x2 = st.ox2[g]; p.x3 = st.sx3[g];
+                    p.y1 = __ldcg(yn + g); p.y2 = __ldcg(yn + yn_stride + g); p.y3 = __ldcg(yn + 2 * yn_stride + g);
+                    mirror_shoulder(p);
+                    st.sx1[g] = p.x1; st.sx3[g] = p.x3;
+                    st.sy1[g] = p.y1; st.sy2[g] = p.y2; st.sy3[g] = p.y3;
+                    double sfhw, hw2, maxp;
+                    solve_stencil(p, sfhw, hw2, maxp);  // :61-64
+                    pout[3 * g] = sfhw; pout[3 * g + 1] = hw2; pout[3 * g + 2] = maxp;
+                }
+            }
         }
     } else {
         const int ph = role - 1;
